@@ -1,0 +1,382 @@
+// analysis.cpp -- host-side integer analysis (see layout.hpp for the reference counterparts).
+#include "layout.hpp"
+
+#include "../../include/opmb200.h"
+
+#include <algorithm>
+#include <numeric>
+
+namespace opmb200 {
+
+namespace {
+inline int64_t find_in_row(const int32_t* rowptr, const int32_t* col, int64_t i, int32_t j)
+{
+    const int32_t* b = col + rowptr[i];
+    const int32_t* e = col + rowptr[i + 1];
+    const int32_t* it = std::lower_bound(b, e, j);
+    return (it != e && *it == j) ? (it - col) : -1;
+}
+} // namespace
+
+// Opm::getMatrixRowColoring: level[i] = 1 + max level over the rows i depends on; rows of a
+// level keep their natural order (stable sort == counting sort).
+int row_coloring(int64_t n, const int32_t* rowptr, const int32_t* col, int type, int32_t* color,
+                 int32_t* level_rows, int32_t* level_ptr)
+{
+    if (type < 0 || type > 2)
+        return -OPMB200_INVALID_ARGUMENT;
+    std::fill(color, color + n, 0);
+    int32_t nlev = 0;
+    if (type == 2) { // UPPER: dependencies on the entries right of the diagonal, rows descending
+        for (int64_t i = n - 1; i >= 0; --i) {
+            const int64_t kd = find_in_row(rowptr, col, i, (int32_t)i);
+            if (kd < 0)
+                return -OPMB200_DIAGONAL_MISSING;
+            int32_t c = 0;
+            for (int64_t k = kd + 1; k < rowptr[i + 1]; ++k)
+                c = std::max(c, color[col[k]] + 1);
+            color[i] = c;
+            nlev = std::max(nlev, c + 1);
+        }
+    } else { // LOWER / SYMMETRIC: entries left of the diagonal, rows ascending
+        for (int64_t i = 0; i < n; ++i) {
+            int32_t c = 0;
+            int64_t k = rowptr[i];
+            for (; k < rowptr[i + 1] && col[k] != i; ++k) {
+                const int32_t j = col[k];
+                if (type == 0 && find_in_row(rowptr, col, j, (int32_t)i) < 0)
+                    continue; // SYMMETRIC: only when A_ji is stored as well
+                c = std::max(c, color[j] + 1);
+            }
+            if (k == rowptr[i + 1])
+                return -OPMB200_DIAGONAL_MISSING; // the reference walks until it meets the diagonal
+            color[i] = c;
+            nlev = std::max(nlev, c + 1);
+        }
+    }
+    std::vector<int32_t> cnt(nlev + 1, 0);
+    for (int64_t i = 0; i < n; ++i)
+        ++cnt[color[i] + 1];
+    for (int32_t l = 0; l < nlev; ++l)
+        cnt[l + 1] += cnt[l];
+    for (int32_t l = 0; l <= nlev; ++l)
+        level_ptr[l] = cnt[l];
+    for (int64_t i = 0; i < n; ++i)
+        level_rows[cnt[color[i]]++] = (int32_t)i;
+    return nlev;
+}
+
+void partition_simple(int32_t num_cells, int32_t num_domains, int32_t* part)
+{
+    // Opm::partitionCellsSimple: num_cells / num_domains each, the first (num_cells mod
+    // num_domains) domains get one more; contiguous in the natural ordering.
+    const int32_t q = num_cells / num_domains, r = num_cells % num_domains;
+    int32_t c = 0;
+    for (int32_t d = 0; d < num_domains; ++d)
+        for (int32_t e = c + q + (d < r ? 1 : 0); c < e; ++c)
+            part[c] = d;
+}
+
+int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const int32_t* col, int64_t n_interior,
+                 bool want_ilu0, Layout& L, std::string& err)
+{
+    if (b < 1 || b > 4) {
+        err = "block size must be 1..4";
+        return OPMB200_INVALID_ARGUMENT;
+    }
+    if (n < 0 || n_interior < 0 || n_interior > n || !rowptr || (!col && nnzb > 0) || rowptr[0] != 0
+        || rowptr[n] != nnzb || nnzb >= (int64_t(1) << 31) - 64 * kSlice) {
+        err = "inconsistent BCSR arguments";
+        return OPMB200_INVALID_ARGUMENT;
+    }
+    L.b = b;
+    L.n = n;
+    L.nnzb = nnzb;
+    L.n_interior = n_interior;
+
+    // ---- validation + diagonal positions ----------------------------------------------------
+    std::vector<int32_t> diag(n);
+    for (int64_t i = 0; i < n; ++i) {
+        if (rowptr[i + 1] < rowptr[i]) {
+            err = "rowptr not monotone";
+            return OPMB200_INVALID_ARGUMENT;
+        }
+        int64_t kd = -1;
+        for (int64_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            if (col[k] < 0 || col[k] >= n || (k > rowptr[i] && col[k] <= col[k - 1])) {
+                err = "column indices must be ascending and in range (row " + std::to_string(i) + ")";
+                return OPMB200_INVALID_ARGUMENT;
+            }
+            if (col[k] == i)
+                kd = k;
+        }
+        if (kd < 0) {
+            err = "diagonal entry missing in row " + std::to_string(i);
+            return OPMB200_DIAGONAL_MISSING;
+        }
+        diag[i] = (int32_t)kd;
+    }
+
+    // ---- reference-exact LOWER colouring of the pattern as given ----------------------------
+    {
+        std::vector<int32_t> color(n);
+        L.ref_level_rows.resize(n);
+        L.ref_level_ptr.resize(n + 1);
+        const int nl = row_coloring(n, rowptr, col, 1, color.data(), L.ref_level_rows.data(), L.ref_level_ptr.data());
+        if (nl < 0) {
+            err = "diagonal entry missing";
+            return -nl;
+        }
+        L.ref_level_ptr.resize(nl + 1);
+    }
+
+    // ---- schedule levels on pattern(A) U pattern(A^T), ghost rows reduced to their diagonal ---
+    // entry (r,c) of an owner row: c < r  => r waits for c ; c > r => c waits for r.
+    auto row_begin = [&](int64_t i) { return i < n_interior ? (int64_t)rowptr[i] : (int64_t)diag[i]; };
+    auto row_end = [&](int64_t i) { return i < n_interior ? (int64_t)rowptr[i + 1] : (int64_t)diag[i] + 1; };
+    std::vector<int32_t> lev(n, 0);
+    bool symmetric = true;
+    for (int64_t r = 0; r < n; ++r) {
+        for (int64_t k = row_begin(r); k < row_end(r); ++k) {
+            const int32_t c = col[k];
+            if (c < r)
+                lev[r] = std::max(lev[r], lev[c] + 1);
+        }
+        for (int64_t k = row_begin(r); k < row_end(r); ++k) {
+            const int32_t c = col[k];
+            if (c > r)
+                lev[c] = std::max(lev[c], lev[r] + 1);
+            if (c != r && c < n_interior && r < n_interior && symmetric && find_in_row(rowptr, col, c, (int32_t)r) < 0)
+                symmetric = false;
+        }
+    }
+    L.symmetric = symmetric;
+    int32_t nlev = 0;
+    for (int64_t i = 0; i < n; ++i)
+        nlev = std::max(nlev, lev[i] + 1);
+    if (n == 0)
+        nlev = 0;
+    L.n_levels = nlev;
+    L.level_q0.assign(nlev + 1, 0);
+    for (int64_t i = 0; i < n; ++i)
+        ++L.level_q0[lev[i] + 1];
+    for (int32_t l = 0; l < nlev; ++l)
+        L.level_q0[l + 1] += L.level_q0[l];
+    L.r2n.resize(n);
+    L.n2r.resize(n);
+    {
+        std::vector<int32_t> cur(L.level_q0.begin(), L.level_q0.end());
+        for (int64_t i = 0; i < n; ++i) {
+            const int32_t q = cur[lev[i]]++;
+            L.r2n[q] = (int32_t)i;
+            L.n2r[i] = q;
+        }
+    }
+
+    // ---- slices --------------------------------------------------------------------------------
+    L.slice_q0.clear();
+    L.slice_level.clear();
+    L.level_slice0.assign(nlev + 1, 0);
+    for (int32_t l = 0; l < nlev; ++l) {
+        L.level_slice0[l] = (int32_t)L.slice_level.size();
+        for (int32_t q = L.level_q0[l]; q < L.level_q0[l + 1]; q += kSlice) {
+            L.slice_q0.push_back(q);
+            L.slice_level.push_back(l);
+        }
+    }
+    L.level_slice0[nlev] = (int32_t)L.slice_level.size();
+    L.n_slices = (int)L.slice_level.size();
+    L.slice_q0.push_back((int32_t)n);
+    L.slice_wl.assign(L.n_slices, 0);
+    L.slice_wu.assign(L.n_slices, 0);
+    L.slice_base.assign(L.n_slices + 1, 0);
+    L.slice_lrank.assign(L.n_slices + 1, 0);
+    for (int s = 0; s < L.n_slices; ++s) {
+        int wl = 0, wu = 0;
+        for (int32_t q = L.slice_q0[s]; q < L.slice_q0[s + 1]; ++q) {
+            const int64_t i = L.r2n[q];
+            if (i < n_interior) {
+                wl = std::max<int>(wl, diag[i] - rowptr[i]);
+                wu = std::max<int>(wu, rowptr[i + 1] - 1 - diag[i]);
+            }
+        }
+        L.slice_wl[s] = wl;
+        L.slice_wu[s] = wu;
+        L.slice_base[s + 1] = L.slice_base[s] + wl + 1 + wu;
+        L.slice_lrank[s + 1] = L.slice_lrank[s] + wl;
+        if ((int64_t)L.slice_base[s] + wl + 1 + wu >= (int64_t(1) << 31) / kSlice) {
+            err = "matrix too large for 32-bit slot ids";
+            return OPMB200_INVALID_ARGUMENT;
+        }
+    }
+    L.n_slot_rows = L.slice_base[L.n_slices];
+
+    // ---- slots -----------------------------------------------------------------------------------
+    const int64_t nslots = L.n_slot_rows * kSlice;
+    L.slot_col.assign(nslots, -1);
+    L.slot_src.assign(nslots, -1);
+    std::vector<int32_t> slot_of_native(nnzb, -1);
+    for (int s = 0; s < L.n_slices; ++s) {
+        const int64_t base = L.slice_base[s];
+        const int wl = L.slice_wl[s];
+        for (int32_t q = L.slice_q0[s]; q < L.slice_q0[s + 1]; ++q) {
+            const int lane = q - L.slice_q0[s];
+            const int64_t i = L.r2n[q];
+            const int64_t gd = (base + wl) * kSlice + lane;
+            L.slot_col[gd] = q;
+            if (i >= n_interior) {
+                L.slot_src[gd] = -2; // ghost row: identity (ISTLSolver.cpp:56-75)
+                continue;
+            }
+            L.slot_src[gd] = diag[i];
+            slot_of_native[diag[i]] = (int32_t)gd;
+            int sl = 0;
+            for (int64_t k = rowptr[i]; k < diag[i]; ++k, ++sl) { // L: ascending column
+                const int64_t g = (base + sl) * kSlice + lane;
+                L.slot_col[g] = L.n2r[col[k]];
+                L.slot_src[g] = (int32_t)k;
+                slot_of_native[k] = (int32_t)g;
+            }
+            int su = 0;
+            for (int64_t k = rowptr[i + 1] - 1; k > diag[i]; --k, ++su) { // U: descending column
+                const int64_t g = (base + wl + 1 + su) * kSlice + lane;
+                L.slot_col[g] = L.n2r[col[k]];
+                L.slot_src[g] = (int32_t)k;
+                slot_of_native[k] = (int32_t)g;
+            }
+        }
+    }
+
+    // ---- DILU transposed-entry map and ILU0 update pairs -------------------------------------------
+    const int64_t nl = L.n_l_slot_rows() * kSlice;
+    L.l_transpose.assign(nl, -1);
+    if (want_ilu0)
+        L.trip_ptr.assign(nl + 1, 0);
+    L.trip_src.clear();
+    L.trip_dst.clear();
+    for (int pass = 0; pass < (want_ilu0 ? 2 : 1); ++pass) {
+        // pass 0: transposes + pair counts ; pass 1: fill pairs
+        for (int s = 0; s < L.n_slices; ++s) {
+            for (int32_t q = L.slice_q0[s]; q < L.slice_q0[s + 1]; ++q) {
+                const int lane = q - L.slice_q0[s];
+                const int64_t i = L.r2n[q];
+                if (i >= n_interior)
+                    continue;
+                int sl = 0;
+                for (int64_t kij = rowptr[i]; kij < diag[i]; ++kij, ++sl) {
+                    const int64_t cl = ((int64_t)L.slice_lrank[s] + sl) * kSlice + lane; // compact L slot
+                    const int32_t j = col[kij];
+                    if (pass == 0) {
+                        const int64_t kji = find_in_row(rowptr, col, j, (int32_t)i);
+                        L.l_transpose[cl] = kji >= 0 ? slot_of_native[kji] : -1;
+                    }
+                    if (!want_ilu0)
+                        continue;
+                    // ParallelOverlappingILU0_impl.hpp:66-86: merge row j (right of its diagonal)
+                    // with row i (right of ij)
+                    int64_t jk = diag[j] + 1, ik = kij + 1;
+                    int32_t w = pass ? L.trip_ptr[cl] : 0;
+                    while (ik < rowptr[i + 1] && jk < rowptr[j + 1]) {
+                        if (col[ik] == col[jk]) {
+                            if (pass) {
+                                L.trip_src[w] = slot_of_native[jk];
+                                L.trip_dst[w] = slot_of_native[ik];
+                            }
+                            ++w;
+                            ++ik;
+                            ++jk;
+                        } else if (col[ik] < col[jk]) {
+                            ++ik;
+                        } else {
+                            ++jk;
+                        }
+                    }
+                    if (!pass)
+                        L.trip_ptr[cl + 1] = w; // count, prefix-summed below
+                }
+            }
+        }
+        if (want_ilu0 && pass == 0) {
+            int64_t tot = 0;
+            for (int64_t c = 0; c < nl; ++c) {
+                const int32_t cnt = L.trip_ptr[c + 1];
+                L.trip_ptr[c] = (int32_t)tot;
+                tot += cnt;
+                if (tot >= (int64_t(1) << 31)) {
+                    err = "too many ILU0 update pairs";
+                    return OPMB200_INVALID_ARGUMENT;
+                }
+            }
+            // shift: trip_ptr[c] now holds starts; rebuild the n+1 form
+            std::vector<int32_t> starts(L.trip_ptr.begin(), L.trip_ptr.begin() + nl);
+            for (int64_t c = 0; c < nl; ++c)
+                L.trip_ptr[c] = starts[c];
+            L.trip_ptr[nl] = (int32_t)tot;
+            L.trip_src.assign(tot, -1);
+            L.trip_dst.assign(tot, -1);
+        }
+    }
+    return OPMB200_SUCCESS;
+}
+
+int localize(int64_t n_global, const int32_t* rowptr, const int32_t* col, const int32_t* part, int32_t rank,
+             int64_t* n_local, int64_t* n_interior, int64_t* nnzb_local, int32_t* out_l2g, int32_t* out_rowptr,
+             int32_t* out_col, int64_t* out_src)
+{
+    std::vector<int32_t> owners, ghosts;
+    std::vector<char> is_ghost(n_global, 0);
+    int64_t nnz = 0;
+    for (int64_t g = 0; g < n_global; ++g) {
+        if (part[g] != rank)
+            continue;
+        owners.push_back((int32_t)g);
+        nnz += rowptr[g + 1] - rowptr[g];
+        for (int64_t k = rowptr[g]; k < rowptr[g + 1]; ++k)
+            if (part[col[k]] != rank)
+                is_ghost[col[k]] = 1;
+    }
+    for (int64_t g = 0; g < n_global; ++g)
+        if (is_ghost[g])
+            ghosts.push_back((int32_t)g);
+    *n_interior = (int64_t)owners.size();
+    *n_local = (int64_t)(owners.size() + ghosts.size());
+    *nnzb_local = nnz + (int64_t)ghosts.size();
+    if (!out_l2g)
+        return OPMB200_SUCCESS;
+    std::vector<int32_t> g2l(n_global, -1);
+    int32_t l = 0;
+    for (int32_t g : owners) {
+        out_l2g[l] = g;
+        g2l[g] = l++;
+    }
+    for (int32_t g : ghosts) {
+        out_l2g[l] = g;
+        g2l[g] = l++;
+    }
+    int64_t w = 0;
+    out_rowptr[0] = 0;
+    std::vector<std::pair<int32_t, int64_t>> tmp;
+    for (size_t li = 0; li < owners.size(); ++li) {
+        const int64_t g = owners[li];
+        tmp.clear();
+        for (int64_t k = rowptr[g]; k < rowptr[g + 1]; ++k)
+            tmp.emplace_back(g2l[col[k]], k);
+        std::sort(tmp.begin(), tmp.end());
+        for (auto& pr : tmp) {
+            out_col[w] = pr.first;
+            out_src[w] = pr.second;
+            ++w;
+        }
+        out_rowptr[li + 1] = (int32_t)w;
+    }
+    for (size_t gi = 0; gi < ghosts.size(); ++gi) {
+        const int32_t li = (int32_t)(owners.size() + gi);
+        out_col[w] = li;
+        out_src[w] = -1;
+        ++w;
+        out_rowptr[li + 1] = (int32_t)w;
+    }
+    return OPMB200_SUCCESS;
+}
+
+} // namespace opmb200

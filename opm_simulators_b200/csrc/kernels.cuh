@@ -1,0 +1,1074 @@
+// kernels.cuh -- hand-written sm_100a kernels of the hot path.
+//
+//   relayout_kernel      caller's BCSR values -> level-ordered SELL-32 (+ ghost rows -> identity)
+//   spmv_kernel          y = A x | y += alpha A x, fused (u,y) and (y,y) partial dots
+//   dilu_factor_kernel   Dinv_i = (A_ii - sum A_ij Dinv_j A_ji)^-1        (DILU.hpp:186-206)
+//   ilu0_factor_kernel   block ILU(0), left-looking, stored inverse        (ParallelOverlappingILU0_impl.hpp:42-99)
+//   sweep_kernel         lower / upper triangular sweeps of DILU and ILU0  (DILU.hpp:253-304, ..ILU0_impl.hpp:383-411)
+//   vec_* kernels        fused BiCGSTAB vector updates + dots, fixed-order reductions
+//
+// All matrix kernels use one lane per block row and one warp per 32-row slice; every matrix
+// load is a warp-wide contiguous 256-byte line (layout.hpp).  The triangular kernels are
+// "sync-free": slices are started strictly in schedule order (atomic ticket), a row spins on
+// the values of the rows it depends on (a NaN-pattern sentinel marks "not yet written"), so no
+// grid-wide barrier and no kernel launch per level is paid.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace opmb200 {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kCtaThreads = kWarpsPerCta * 32;
+constexpr unsigned long long kSentinelBits = 0xFFF8B200DEADC0DEull; // quiet NaN never produced by arithmetic
+
+struct SliceMeta { // 32 bytes
+    int q0, count, base, wl, wu, level, lrank, pad;
+};
+
+// device-resident scalar state of one BiCGSTAB solve (Dune::BiCGSTABSolver::apply locals)
+struct Scalars {
+    double rho, rho_new, alpha, omega, beta, h, norm, norm0;
+    double reduction; // requested |r|/|r0|
+    double it;        // Dune's half-step counter
+    int maxiter;
+    int converged;
+    int abort_code; // 0 ok, 1 breakdown (rho/omega/h), 2 NaN/Inf defect
+    int done;       // converged || abort || out of iterations  => all later kernels return at once
+    int hist_count;
+    int hist_cap;
+    int factor_error; // singular diagonal block seen by a factorisation kernel
+    int pad;
+};
+
+enum Epilogue { EPI_NONE = 0, EPI_INIT = 1, EPI_H = 2, EPI_NORM1 = 3, EPI_OMEGA = 4, EPI_NORM2 = 5, EPI_DOT = 6 };
+
+// -------------------------------------------------------------------------------------------------
+// small helpers
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ld_relaxed(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(double* p, double v)
+{
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(int* p, int v)
+{
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ bool is_sentinel(double v)
+{
+    return (unsigned long long)__double_as_longlong(v) == kSentinelBits;
+}
+__device__ __forceinline__ double sentinel() { return __longlong_as_double((long long)kSentinelBits); }
+// a genuine result that happens to carry the sentinel bit pattern is stored as the canonical NaN
+__device__ __forceinline__ double guard(double v)
+{
+    return is_sentinel(v) ? __longlong_as_double(0x7FF8000000000000ll) : v;
+}
+
+// element e of block slot (slot_row, lane)
+template <int BB>
+__device__ __forceinline__ size_t elem_index(int slot_row, int lane, int e)
+{
+    return (size_t)slot_row * (32 * BB) + (size_t)e * 32 + lane;
+}
+template <int BB>
+__device__ __forceinline__ size_t elem_index_slot(int g, int e)
+{
+    return (size_t)(g & ~31) * BB + (size_t)e * 32 + (g & 31);
+}
+
+// y -= A x ; y += A x ; y = A x     (row-major b x b, Dune mmv / umv / mv)
+template <int B>
+__device__ __forceinline__ void blk_mmv(const double* A, const double* x, double* y)
+{
+#pragma unroll
+    for (int r = 0; r < B; ++r)
+#pragma unroll
+        for (int c = 0; c < B; ++c)
+            y[r] -= A[r * B + c] * x[c];
+}
+template <int B>
+__device__ __forceinline__ void blk_umv(const double* A, const double* x, double* y)
+{
+#pragma unroll
+    for (int r = 0; r < B; ++r)
+#pragma unroll
+        for (int c = 0; c < B; ++c)
+            y[r] += A[r * B + c] * x[c];
+}
+template <int B>
+__device__ __forceinline__ void blk_mv(const double* A, const double* x, double* y)
+{
+#pragma unroll
+    for (int r = 0; r < B; ++r) {
+        double s = 0.0;
+#pragma unroll
+        for (int c = 0; c < B; ++c)
+            s += A[r * B + c] * x[c];
+        y[r] = s;
+    }
+}
+template <int B>
+__device__ __forceinline__ void blk_mm(const double* A, const double* Bm, double* C)
+{
+#pragma unroll
+    for (int i = 0; i < B; ++i)
+#pragma unroll
+        for (int j = 0; j < B; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < B; ++k)
+                s += A[i * B + k] * Bm[k * B + j];
+            C[i * B + j] = s;
+        }
+}
+
+// Opm::MatrixBlock::invert (matrixblock.hh:255-283).  Returns false for an exactly singular 4x4
+// block (the only case in which the reference throws Dune::MatrixBlockError).
+template <int B>
+__device__ __forceinline__ bool blk_invert(double* a);
+
+template <>
+__device__ __forceinline__ bool blk_invert<1>(double* a)
+{
+    a[0] = 1.0 / a[0];
+    return true;
+}
+template <>
+__device__ __forceinline__ bool blk_invert<2>(double* a)
+{
+    const double det_1 = 1.0 / (a[0] * a[3] - a[1] * a[2]);
+    const double a00 = a[0];
+    a[0] = a[3] * det_1;
+    a[1] = -a[1] * det_1;
+    a[2] = -a[2] * det_1;
+    a[3] = a00 * det_1;
+    return true;
+}
+template <>
+__device__ __forceinline__ bool blk_invert<3>(double* a)
+{
+    // Dune::FMatrixHelp::invertMatrix 3x3 closed form (same expression tree as
+    // gpuistl/detail/deviceBlockOperations.hpp:51-72)
+    const double m00 = a[0], m01 = a[1], m02 = a[2], m10 = a[3], m11 = a[4], m12 = a[5], m20 = a[6], m21 = a[7],
+                 m22 = a[8];
+    const double p0011 = m00 * m11, p0012 = m00 * m12, p0110 = m01 * m10, p0210 = m02 * m10, p0120 = m01 * m20,
+                 p0220 = m02 * m20;
+    const double rdet
+        = 1.0 / (p0011 * m22 - p0012 * m21 - p0110 * m22 + p0210 * m21 + p0120 * m12 - p0220 * m11);
+    a[0] = (m11 * m22 - m12 * m21) * rdet;
+    a[1] = -(m01 * m22 - m02 * m21) * rdet;
+    a[2] = (m01 * m12 - m02 * m11) * rdet;
+    a[3] = -(m10 * m22 - m12 * m20) * rdet;
+    a[4] = (m00 * m22 - p0220) * rdet;
+    a[5] = -(p0012 - p0210) * rdet;
+    a[6] = (m10 * m21 - m11 * m20) * rdet;
+    a[7] = -(m00 * m21 - p0120) * rdet;
+    a[8] = (p0011 - p0110) * rdet;
+    return true;
+}
+// Dune DenseMatrix::invert: LU with partial pivoting, singular iff a pivot is exactly zero
+__device__ inline bool blk_invert_lu4(double* M)
+{
+    double A[16];
+    int piv[4];
+    for (int i = 0; i < 16; ++i)
+        A[i] = M[i];
+    for (int i = 0; i < 4; ++i) {
+        double pivmax = fabs(A[i * 4 + i]);
+        int imax = i;
+        for (int k = i + 1; k < 4; ++k) {
+            const double v = fabs(A[k * 4 + i]);
+            if (v > pivmax) {
+                pivmax = v;
+                imax = k;
+            }
+        }
+        if (imax != i)
+            for (int j = 0; j < 4; ++j) {
+                const double t = A[i * 4 + j];
+                A[i * 4 + j] = A[imax * 4 + j];
+                A[imax * 4 + j] = t;
+            }
+        piv[i] = imax;
+        if (!(pivmax != 0.0))
+            return false;
+        for (int k = i + 1; k < 4; ++k) {
+            const double f = A[k * 4 + i] / A[i * 4 + i];
+            A[k * 4 + i] = f;
+            for (int j = i + 1; j < 4; ++j)
+                A[k * 4 + j] -= f * A[i * 4 + j];
+        }
+    }
+    for (int i = 0; i < 16; ++i)
+        M[i] = 0.0;
+    for (int i = 0; i < 4; ++i)
+        M[i * 4 + i] = 1.0;
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < i; ++j)
+            for (int k = 0; k < 4; ++k)
+                M[i * 4 + k] -= A[i * 4 + j] * M[j * 4 + k];
+    for (int i = 3; i >= 0; --i)
+        for (int k = 0; k < 4; ++k) {
+            for (int j = i + 1; j < 4; ++j)
+                M[i * 4 + k] -= A[i * 4 + j] * M[j * 4 + k];
+            M[i * 4 + k] /= A[i * 4 + i];
+        }
+    for (int i = 3; i >= 0; --i)
+        if (i != piv[i])
+            for (int j = 0; j < 4; ++j) {
+                const double t = M[j * 4 + i];
+                M[j * 4 + i] = M[j * 4 + piv[i]];
+                M[j * 4 + piv[i]] = t;
+            }
+    return true;
+}
+template <>
+__device__ __forceinline__ bool blk_invert<4>(double* a)
+{
+    // adjugate / determinant with the term order of matrixblock.hh:72-190; pivoted-LU fallback
+    // for |det| < 1e-40 (:205-224)
+    double m[16], inv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        m[i] = a[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // rows != j, cols != i
+            const int r0 = (j == 0) ? 1 : 0, r1 = (j <= 1) ? 2 : 1, r2 = (j <= 2) ? 3 : 2;
+            const int c0 = (i == 0) ? 1 : 0, c1 = (i <= 1) ? 2 : 1, c2 = (i <= 2) ? 3 : 2;
+            const double sg = ((i + j) & 1) ? -1.0 : 1.0;
+            double s = sg * m[r0 * 4 + c0] * m[r1 * 4 + c1] * m[r2 * 4 + c2];
+            s -= sg * m[r0 * 4 + c0] * m[r1 * 4 + c2] * m[r2 * 4 + c1];
+            s -= sg * m[r1 * 4 + c0] * m[r0 * 4 + c1] * m[r2 * 4 + c2];
+            s += sg * m[r1 * 4 + c0] * m[r0 * 4 + c2] * m[r2 * 4 + c1];
+            s += sg * m[r2 * 4 + c0] * m[r0 * 4 + c1] * m[r1 * 4 + c2];
+            s -= sg * m[r2 * 4 + c0] * m[r0 * 4 + c2] * m[r1 * 4 + c1];
+            inv[i * 4 + j] = s;
+        }
+    const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+    if (fabs(det) < 1e-40) {
+        if (!blk_invert_lu4(a)) {
+            for (int k = 0; k < 16; ++k)
+                a[k] = __longlong_as_double(0x7FF8000000000000ll);
+            return false;
+        }
+        return true;
+    }
+    const double rdet = 1.0 / det;
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        a[k] = inv[k] * rdet;
+    return true;
+}
+
+// -------------------------------------------------------------------------------------------------
+// fixed-order reductions.  Every CTA reduces its threads' contributions with a shuffle tree and
+// a fixed cross-warp order and writes one partial per dot; the LAST CTA to finish (atomic
+// counter) sums the partials in index order with the same tree and runs the scalar epilogue.
+// The summation order therefore depends on the launch geometry only, never on scheduling.
+// -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int ND>
+__device__ __forceinline__ void cta_sum(double (&v)[ND], double* smem /* [ND][32] */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        v[d] = warp_sum(v[d]);
+        if (lane == 0)
+            smem[d * 32 + warp] = v[d];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            double t = lane < nw ? smem[d * 32 + lane] : 0.0;
+            v[d] = warp_sum(t);
+        }
+    }
+}
+
+struct ReduceCtx {
+    double* partials;      // [ND][max grid]
+    unsigned int* counter; // self-resetting arrival counter
+    int stride;            // max grid
+    double* sums;          // multi-rank: the local sums land here, an NCCL all-reduce and
+    int defer;             //   epilogue_kernel follow on the stream (defer != 0)
+};
+
+__device__ void run_epilogue(int epi, Scalars* sc, double* hist, const double* s, double* dot_out)
+{
+    const double EPSILON = 1e-80; // dune-istl BiCGSTABSolver breakdown threshold
+    switch (epi) {
+    case EPI_INIT: { // norm0 = |r|, rt = r  =>  rho_new = (rt, r) = |r|^2
+        const double nrm = sqrt(s[0]);
+        sc->norm0 = nrm;
+        sc->norm = nrm;
+        sc->it = 0.0;
+        sc->rho = 1.0;
+        sc->alpha = 1.0;
+        sc->omega = 1.0;
+        sc->beta = 0.0;
+        sc->rho_new = s[0];
+        sc->hist_count = 0;
+        if (sc->hist_cap > 0)
+            hist[sc->hist_count++] = nrm;
+        if (!isfinite(nrm)) {
+            sc->abort_code = 2;
+            sc->done = 1;
+        } else if (nrm < nrm * sc->reduction || nrm < 1e-30) {
+            sc->converged = 1;
+            sc->done = 1;
+        } else if (!(0.5 < sc->maxiter)) {
+            sc->done = 1;
+        }
+        break;
+    }
+    case EPI_H: { // h = (rt, v); alpha = rho_new / h
+        sc->h = s[0];
+        if (fabs(s[0]) < EPSILON) {
+            sc->abort_code = 1;
+            sc->done = 1;
+        }
+        sc->alpha = (sc->norm == 0.0) ? 0.0 : sc->rho_new / s[0];
+        break;
+    }
+    case EPI_NORM1:   // first half step done
+    case EPI_NORM2: { // second half step done; s[1] = (rt, r)
+        const double nrm = sqrt(s[0]);
+        sc->norm = nrm;
+        sc->it += 0.5;
+        if (sc->hist_count < sc->hist_cap)
+            hist[sc->hist_count++] = nrm;
+        if (!isfinite(nrm)) {
+            sc->abort_code = 2;
+            sc->done = 1;
+            break;
+        }
+        if (nrm < sc->norm0 * sc->reduction || nrm < 1e-30) {
+            sc->converged = 1;
+            sc->done = 1;
+            break;
+        }
+        if (epi == EPI_NORM2) {
+            sc->rho = sc->rho_new;
+            sc->rho_new = s[1];
+            if (!(sc->it + 0.5 < sc->maxiter)) { // for (it = 0.5; it < maxit; it += .5)
+                sc->done = 1;
+                break;
+            }
+            // breakdown tests of the next loop head
+            if (fabs(sc->rho) <= EPSILON || fabs(sc->omega) <= EPSILON) {
+                sc->abort_code = 1;
+                sc->done = 1;
+                break;
+            }
+            sc->beta = (nrm == 0.0) ? 0.0 : (sc->rho_new / sc->rho) * (sc->alpha / sc->omega);
+        }
+        break;
+    }
+    case EPI_OMEGA: { // s[0] = (t, r), s[1] = (t, t)
+        sc->omega = (sc->norm == 0.0) ? 0.0 : s[0] / s[1];
+        break;
+    }
+    case EPI_DOT:
+        dot_out[0] = s[0];
+        break;
+    default:
+        break;
+    }
+}
+
+// called by all threads of every CTA with the CTA's thread-local sums
+template <int ND>
+__device__ __forceinline__ void grid_reduce(double (&v)[ND], const ReduceCtx& rc, int epi, Scalars* sc, double* hist,
+                                            double* dot_out)
+{
+    __shared__ double red_smem[ND * 32];
+    __shared__ bool is_last;
+    cta_sum<ND>(v, red_smem);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            rc.partials[d * rc.stride + blockIdx.x] = v[d];
+        __threadfence();
+        const unsigned int t = atomicAdd(rc.counter, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last)
+        return;
+    __threadfence();
+    double acc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        acc[d] = 0.0;
+        for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
+            acc[d] += __ldcg(&rc.partials[d * rc.stride + i]);
+    }
+    __syncthreads();
+    cta_sum<ND>(acc, red_smem);
+    if (threadIdx.x == 0) {
+        *rc.counter = 0u;
+        if (rc.defer) {
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                rc.sums[d] = acc[d];
+        } else {
+            run_epilogue(epi, sc, hist, acc, dot_out);
+        }
+    }
+}
+
+// multi-rank: runs the scalar epilogue on the all-reduced sums
+__global__ void epilogue_kernel(int epi, Scalars* sc, double* hist, const double* sums, double* dot_out, int check_done)
+{
+    if (check_done && sc->done)
+        return;
+    run_epilogue(epi, sc, hist, sums, dot_out);
+}
+
+// -------------------------------------------------------------------------------------------------
+// relayout: caller's BCSR values -> SELL-32 slots (A, and optionally a second copy for ILU0)
+// -------------------------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(256) relayout_kernel(int64_t nslots, const int* __restrict__ slot_src,
+                                                       const double* __restrict__ vals, double* __restrict__ A,
+                                                       double* __restrict__ F)
+{
+    constexpr int BB = B * B;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < nslots; g += (int64_t)gridDim.x * blockDim.x) {
+        const int src = slot_src[g];
+        double blk[BB];
+        if (src >= 0) {
+            const double* p = vals + (size_t)src * BB;
+#pragma unroll
+            for (int e = 0; e < BB; ++e)
+                blk[e] = __ldg(p + e);
+        } else {
+#pragma unroll
+            for (int e = 0; e < BB; ++e)
+                blk[e] = (src == -2 && (e / B) == (e % B)) ? 1.0 : 0.0;
+        }
+        const size_t o = (size_t)(g & ~(int64_t)31) * BB + (g & 31);
+#pragma unroll
+        for (int e = 0; e < BB; ++e) {
+            A[o + (size_t)e * 32] = blk[e];
+            if (F)
+                F[o + (size_t)e * 32] = blk[e];
+        }
+    }
+}
+
+// natural <-> level order for vectors
+template <int B>
+__global__ void permute_in_kernel(int64_t n, const int* __restrict__ r2n, const double* __restrict__ nat,
+                                  double* __restrict__ lvl)
+{
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * B; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = t / B;
+        const int c = (int)(t - q * B);
+        lvl[t] = nat[(size_t)r2n[q] * B + c];
+    }
+}
+template <int B>
+__global__ void permute_out_kernel(int64_t n, const int* __restrict__ n2r, const double* __restrict__ lvl,
+                                   double* __restrict__ nat)
+{
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * B; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / B;
+        const int c = (int)(t - i * B);
+        nat[t] = lvl[(size_t)n2r[i] * B + c];
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// SpMV (MatrixAdapter / GhostLastMatrixAdapter::apply, applyscaleadd; WellOperators.hpp:432-456)
+// -------------------------------------------------------------------------------------------------
+struct SpmvArgs {
+    int nslices;
+    const SliceMeta* slices;
+    const int* slot_col;
+    const double* A;
+    const int* r2n;      // only read when n_interior < n
+    int64_t n, n_interior;
+    const double* x;
+    double* y;
+    double alpha;        // SCALEADD: y += alpha A x
+    const double* u;     // dot 0 partner: (u, y_new)   (NDOT >= 1)
+    double* copy_out;    // optional second destination of y_new (rt = r)
+    ReduceCtx rc;
+    int epi;
+    Scalars* sc;
+    double* hist;
+    double* dot_out;
+    int check_done;
+};
+
+template <int B, bool SCALEADD, int NDOT>
+__global__ void __launch_bounds__(kCtaThreads) spmv_kernel(SpmvArgs a)
+{
+    constexpr int BB = B * B;
+    if (a.check_done && a.sc->done)
+        return;
+    const int lane = threadIdx.x & 31;
+    const int S = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    double acc[B];
+#pragma unroll
+    for (int r = 0; r < B; ++r)
+        acc[r] = 0.0;
+    double dots[NDOT > 0 ? NDOT : 1];
+#pragma unroll
+    for (int d = 0; d < (NDOT > 0 ? NDOT : 1); ++d)
+        dots[d] = 0.0;
+    if (S < a.nslices) {
+        const SliceMeta m = a.slices[S];
+        const bool active = lane < m.count;
+        const int q = m.q0 + lane;
+        const int nsr = m.wl + 1 + m.wu;
+#pragma unroll 2
+        for (int sr = 0; sr < nsr; ++sr) {
+            const int c = active ? __ldg(a.slot_col + (size_t)(m.base + sr) * 32 + lane) : -1;
+            if (c >= 0) {
+                double blk[BB], xv[B];
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    blk[e] = __ldcs(a.A + elem_index<BB>(m.base + sr, lane, e));
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    xv[r] = __ldg(a.x + (size_t)c * B + r);
+                blk_umv<B>(blk, xv, acc);
+            }
+        }
+        if (active) {
+            const bool ghost = (a.n_interior < a.n) && (a.r2n[q] >= a.n_interior);
+            double out[B];
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                double v = ghost ? 0.0 : acc[r];
+                if (SCALEADD)
+                    v = ghost ? 0.0 : a.y[(size_t)q * B + r] + a.alpha * v;
+                out[r] = v;
+                a.y[(size_t)q * B + r] = v;
+                if (a.copy_out)
+                    a.copy_out[(size_t)q * B + r] = v;
+            }
+            if (NDOT >= 1) {
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    dots[0] += out[r] * (a.u ? a.u[(size_t)q * B + r] : out[r]);
+            }
+            if (NDOT >= 2) {
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    dots[NDOT >= 2 ? 1 : 0] += out[r] * out[r];
+            }
+        }
+    }
+    if (NDOT > 0)
+        grid_reduce<(NDOT > 0 ? NDOT : 1)>(dots, a.rc, a.epi, a.sc, a.hist, a.dot_out);
+}
+
+// -------------------------------------------------------------------------------------------------
+// in-order slice scheduling for the dependency-carrying kernels
+// -------------------------------------------------------------------------------------------------
+struct Ticket {
+    unsigned int* next; // next chunk to hand out
+    unsigned int* done; // CTAs finished (the last one rewinds both counters)
+};
+
+// returns the chunk index of this CTA: CTAs obtain chunks in the order they START running, so a
+// CTA only ever waits for chunks held by CTAs that are already resident (no deadlock, whatever
+// order the hardware dispatches blockIdx in).
+__device__ __forceinline__ unsigned int take_ticket(const Ticket& t)
+{
+    __shared__ unsigned int chunk;
+    if (threadIdx.x == 0)
+        chunk = atomicAdd(t.next, 1u);
+    __syncthreads();
+    return chunk;
+}
+__device__ __forceinline__ void return_ticket(const Ticket& t)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(t.done, 1u) == gridDim.x - 1) {
+            *t.next = 0u;
+            *t.done = 0u;
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// DILU factorisation  (MultithreadDILU::update, DILU.hpp:186-206 / 208-251)
+//   Dinv_i = (A_ii - sum_{j<i, A_ji stored} (A_ij Dinv_j) A_ji)^-1
+// readiness of Dinv_j is published through row_flag[j] == epoch (release/acquire).
+// -------------------------------------------------------------------------------------------------
+struct FactorArgs {
+    int nslices;
+    const SliceMeta* slices;
+    const int* slot_col;
+    const double* A;        // DILU: matrix values ; ILU0: unused
+    double* F;              // ILU0: factor values, updated in place
+    const int* l_transpose; // DILU
+    const int* trip_ptr;    // ILU0
+    const int* trip_src;
+    const int* trip_dst;
+    double* dinv;           // [n][b*b] by position
+    int* row_flag;          // [n]
+    int epoch;
+    Ticket ticket;
+    Scalars* sc;
+};
+
+template <int BB>
+__device__ __forceinline__ void wait_row(const int* flag, int epoch)
+{
+    while (ld_relaxed(flag) != epoch)
+        __nanosleep(32);
+    __threadfence();
+}
+
+template <int B>
+__global__ void __launch_bounds__(kCtaThreads) dilu_factor_kernel(FactorArgs a)
+{
+    constexpr int BB = B * B;
+    const unsigned int chunk = take_ticket(a.ticket);
+    const int lane = threadIdx.x & 31;
+    const int S = (int)chunk * kWarpsPerCta + (threadIdx.x >> 5);
+    if (S < a.nslices) {
+        const SliceMeta m = a.slices[S];
+        if (lane < m.count) {
+            const int q = m.q0 + lane;
+            double D[BB];
+#pragma unroll
+            for (int e = 0; e < BB; ++e)
+                D[e] = a.A[elem_index<BB>(m.base + m.wl, lane, e)];
+            for (int s = 0; s < m.wl; ++s) {
+                const int c = a.slot_col[(size_t)(m.base + s) * 32 + lane];
+                if (c < 0)
+                    continue;
+                const int tr = a.l_transpose[(size_t)(m.lrank + s) * 32 + lane];
+                if (tr < 0)
+                    continue; // A_ji not stored: no contribution (DILU.hpp:196-201)
+                double Aij[BB], Aji[BB], Dj[BB], T1[BB], T2[BB];
+#pragma unroll
+                for (int e = 0; e < BB; ++e) {
+                    Aij[e] = a.A[elem_index<BB>(m.base + s, lane, e)];
+                    Aji[e] = a.A[elem_index_slot<BB>(tr, e)];
+                }
+                wait_row<BB>(a.row_flag + c, a.epoch);
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    Dj[e] = ld_relaxed(a.dinv + (size_t)c * BB + e);
+                blk_mm<B>(Aij, Dj, T1);
+                blk_mm<B>(T1, Aji, T2);
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    D[e] -= T2[e];
+            }
+            if (!blk_invert<B>(D))
+                a.sc->factor_error = 1;
+#pragma unroll
+            for (int e = 0; e < BB; ++e)
+                st_relaxed(a.dinv + (size_t)q * BB + e, D[e]);
+            __threadfence();
+            st_relaxed(a.row_flag + q, a.epoch);
+        }
+    }
+    return_ticket(a.ticket);
+}
+
+// -------------------------------------------------------------------------------------------------
+// block ILU(0) factorisation, left-looking with stored inverse diagonal
+// (detail::ghost_last_bilu0_decomposition, ParallelOverlappingILU0_impl.hpp:42-99 ==
+//  Dune::ILU::blockILU0Decomposition).  F holds a copy of A on entry and L \ D^-1 \ U on exit.
+// -------------------------------------------------------------------------------------------------
+template <int B>
+__global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
+{
+    constexpr int BB = B * B;
+    const unsigned int chunk = take_ticket(a.ticket);
+    const int lane = threadIdx.x & 31;
+    const int S = (int)chunk * kWarpsPerCta + (threadIdx.x >> 5);
+    if (S < a.nslices) {
+        const SliceMeta m = a.slices[S];
+        if (lane < m.count) {
+            const int q = m.q0 + lane;
+            for (int s = 0; s < m.wl; ++s) {
+                const int c = a.slot_col[(size_t)(m.base + s) * 32 + lane];
+                if (c < 0)
+                    continue;
+                double Aij[BB], Dj[BB], Lij[BB];
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    Aij[e] = ld_relaxed(a.F + elem_index<BB>(m.base + s, lane, e));
+                wait_row<BB>(a.row_flag + c, a.epoch);
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    Dj[e] = ld_relaxed(a.dinv + (size_t)c * BB + e);
+                blk_mm<B>(Aij, Dj, Lij); // L_ij = A_ij A_jj^-1   (rightmultiply, :63)
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    st_relaxed(a.F + elem_index<BB>(m.base + s, lane, e), Lij[e]);
+                const size_t cl = (size_t)(m.lrank + s) * 32 + lane;
+                for (int t = a.trip_ptr[cl]; t < a.trip_ptr[cl + 1]; ++t) { // A_ik -= L_ij A_jk (:66-86)
+                    const int gs = a.trip_src[t], gd = a.trip_dst[t];
+                    double Ujk[BB], P[BB];
+#pragma unroll
+                    for (int e = 0; e < BB; ++e)
+                        Ujk[e] = ld_relaxed(a.F + elem_index_slot<BB>(gs, e));
+                    blk_mm<B>(Lij, Ujk, P);
+#pragma unroll
+                    for (int e = 0; e < BB; ++e) {
+                        double* p = a.F + elem_index_slot<BB>(gd, e);
+                        st_relaxed(p, ld_relaxed(p) - P[e]);
+                    }
+                }
+            }
+            double D[BB];
+#pragma unroll
+            for (int e = 0; e < BB; ++e)
+                D[e] = ld_relaxed(a.F + elem_index<BB>(m.base + m.wl, lane, e));
+            if (!blk_invert<B>(D))
+                a.sc->factor_error = 1;
+#pragma unroll
+            for (int e = 0; e < BB; ++e) {
+                st_relaxed(a.F + elem_index<BB>(m.base + m.wl, lane, e), D[e]);
+                st_relaxed(a.dinv + (size_t)q * BB + e, D[e]);
+            }
+            __threadfence();
+            st_relaxed(a.row_flag + q, a.epoch);
+        }
+    }
+    return_ticket(a.ticket);
+}
+
+// -------------------------------------------------------------------------------------------------
+// triangular sweeps
+//   DILU  lower: y_i = Dinv_i (d_i - sum_{j<i} A_ij y_j)          upper: v_i = y_i - Dinv_i sum_{j>i} A_ij v_j
+//   ILU0  lower: y_i = d_i - sum_{j<i} L_ij y_j                   upper: v_i = w Dinv_i (y_i - sum_{j>i} U_ij v_j)
+// `tmp` carries y between the two kernels.  Protocol: tmp is all-sentinel between applies; the
+// lower kernel arms v with sentinels and fills tmp; the upper kernel consumes tmp (re-arming it)
+// and fills v.  A consumer simply re-reads the value it needs until it is not the sentinel.
+// -------------------------------------------------------------------------------------------------
+struct SweepArgs {
+    int nslices;
+    const SliceMeta* slices;
+    const int* slot_col;
+    const double* M;     // block values (A for DILU, F for ILU0)
+    const double* dinv;  // [n][b*b]
+    const double* d;     // right-hand side (lower)
+    double* tmp;         // y
+    double* v;           // result
+    const int* level_q0; // [n_levels+1]
+    int n_levels;
+    int throttle;        // how many levels behind the front fine-grained polling starts
+    double relax;        // ILU0 relaxation w (1.0: none)
+    const int* r2n;      // ghost detection (ILU0, parallel)
+    int64_t n, n_interior;
+    int ghost_zero;      // ILU0 ghost rows: 1 = v enters as 0 (the solver's y = 0), 0 = keep v's input
+    Ticket ticket;
+    Scalars* sc;
+    int check_done;
+};
+
+constexpr int kPrefetch = 3; // block slots held in registers before the dependency wait
+
+template <int B, bool ILU0, bool UPPER>
+__global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(SweepArgs a)
+{
+    constexpr int BB = B * B;
+    const unsigned int chunk = take_ticket(a.ticket);
+    const bool skip = a.check_done && a.sc->done;
+    const int lane = threadIdx.x & 31;
+    const int Sfwd = (int)chunk * kWarpsPerCta + (threadIdx.x >> 5);
+    const int S = UPPER ? a.nslices - 1 - Sfwd : Sfwd;
+    if (!skip && Sfwd < a.nslices) {
+        const SliceMeta m = a.slices[S];
+        const bool active = lane < m.count;
+        const int q = m.q0 + lane;
+        const int w = UPPER ? m.wu : m.wl;
+        const int sr0 = UPPER ? m.base + m.wl + 1 : m.base;
+        double* out = UPPER ? a.v : a.tmp; // what this sweep produces and what its consumers poll
+
+        // ---- 1. prefetch everything that does not depend on other rows --------------------------
+        int cj[kPrefetch];
+        double blk[kPrefetch][BB];
+#pragma unroll
+        for (int s = 0; s < kPrefetch; ++s)
+            cj[s] = (active && s < w) ? __ldg(a.slot_col + (size_t)(sr0 + s) * 32 + lane) : -1;
+#pragma unroll
+        for (int s = 0; s < kPrefetch; ++s)
+            if (cj[s] >= 0) {
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    blk[s][e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
+            }
+        double di[BB], rhs[B];
+        bool ghost = false;
+        if (active) {
+            if (!(ILU0 && !UPPER)) {
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    di[e] = __ldcs(a.dinv + (size_t)q * BB + e);
+            }
+            if (ILU0 && a.n_interior < a.n)
+                ghost = a.r2n[q] >= a.n_interior;
+            if (!UPPER) {
+                // ParallelOverlappingILU0 never touches ghost rows: their v keeps its input value
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    rhs[r] = ghost ? (a.ghost_zero ? 0.0 : a.v[(size_t)q * B + r]) : a.d[(size_t)q * B + r];
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    st_relaxed(a.v + (size_t)q * B + r, sentinel()); // arm the upper sweep's output
+            } else {
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    rhs[r] = (ILU0) ? a.tmp[(size_t)q * B + r] : 0.0;
+            }
+        }
+
+        // ---- 2. stay asleep while the front is far away (keeps polling traffic off the L2) -------
+        if (a.throttle > 0) {
+            const int lv = UPPER ? m.level + a.throttle : m.level - a.throttle;
+            if (lv >= 0 && lv < a.n_levels) {
+                const int pq = UPPER ? a.level_q0[lv] : a.level_q0[lv + 1] - 1;
+                const double* pp = out + (size_t)pq * B + (B - 1);
+                if (lane == 0)
+                    while (is_sentinel(ld_relaxed(pp)))
+                        __nanosleep(200);
+                __syncwarp();
+            }
+        }
+
+        // ---- 3. wait for the rows this row depends on, then accumulate in slot order ------------
+        if (active) {
+            double xv[kPrefetch][B];
+            unsigned pending = 0;
+#pragma unroll
+            for (int s = 0; s < kPrefetch; ++s)
+                if (cj[s] >= 0)
+                    pending |= 1u << s;
+            while (pending) {
+#pragma unroll
+                for (int s = 0; s < kPrefetch; ++s)
+                    if (pending & (1u << s)) {
+                        bool ok = true;
+#pragma unroll
+                        for (int r = 0; r < B; ++r) {
+                            xv[s][r] = ld_relaxed(out + (size_t)cj[s] * B + r);
+                            ok = ok && !is_sentinel(xv[s][r]);
+                        }
+                        if (ok)
+                            pending &= ~(1u << s);
+                    }
+            }
+#pragma unroll
+            for (int s = 0; s < kPrefetch; ++s)
+                if (cj[s] >= 0) {
+                    if (UPPER && !ILU0)
+                        blk_umv<B>(blk[s], xv[s], rhs);
+                    else
+                        blk_mmv<B>(blk[s], xv[s], rhs);
+                }
+            // rows wider than the register window (NNC / well rows): stream the rest
+            for (int s = kPrefetch; s < w; ++s) {
+                const int c = __ldg(a.slot_col + (size_t)(sr0 + s) * 32 + lane);
+                if (c < 0)
+                    continue;
+                double bl[BB], xs[B];
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    bl[e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
+                bool ok;
+                do {
+                    ok = true;
+#pragma unroll
+                    for (int r = 0; r < B; ++r) {
+                        xs[r] = ld_relaxed(out + (size_t)c * B + r);
+                        ok = ok && !is_sentinel(xs[r]);
+                    }
+                } while (!ok);
+                if (UPPER && !ILU0)
+                    blk_umv<B>(bl, xs, rhs);
+                else
+                    blk_mmv<B>(bl, xs, rhs);
+            }
+
+            // ---- 4. finish the row and publish it ------------------------------------------------
+            double res[B];
+            if (!UPPER) {
+                if (ILU0) {
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+                        res[r] = rhs[r]; // L_ii = I
+                } else {
+                    blk_mv<B>(di, rhs, res); // y_i = Dinv_i rhs
+                }
+            } else {
+                if (ILU0) {
+                    if (ghost) {
+#pragma unroll
+                        for (int r = 0; r < B; ++r)
+                            res[r] = rhs[r];
+                    } else {
+                        blk_mv<B>(di, rhs, res); // v_i = Dinv_i (y_i - sum)
+#pragma unroll
+                        for (int r = 0; r < B; ++r)
+                            res[r] *= a.relax;
+                    }
+                } else {
+                    double yi[B];
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+                        yi[r] = a.tmp[(size_t)q * B + r];
+                    blk_mmv<B>(di, rhs, yi); // v_i = y_i - Dinv_i rhs
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+                        res[r] = yi[r];
+                }
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    a.tmp[(size_t)q * B + r] = sentinel(); // re-arm for the next apply
+            }
+#pragma unroll
+            for (int r = 0; r < B; ++r)
+                st_relaxed(out + (size_t)q * B + r, guard(res[r]));
+        }
+    }
+    return_ticket(a.ticket);
+}
+
+// -------------------------------------------------------------------------------------------------
+// fused BiCGSTAB vector kernels (Dune::BiCGSTABSolver::apply; one pass each, dots fused)
+// -------------------------------------------------------------------------------------------------
+struct VecArgs {
+    int64_t len; // n * b
+    double* x;
+    double* r;
+    double* p;
+    const double* v;
+    const double* t;
+    const double* y;
+    const double* rt;
+    ReduceCtx rc;
+    Scalars* sc;
+    double* hist;
+};
+
+// p = r + beta (p - omega v)          (first iteration: beta = 0, p = v = 0  =>  p = r)
+__global__ void __launch_bounds__(256) vec_p_update_kernel(VecArgs a)
+{
+    if (a.sc->done)
+        return;
+    const double beta = a.sc->beta, omega = a.sc->omega;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.len; i += (int64_t)gridDim.x * blockDim.x) {
+        double pn = a.p[i] - omega * a.v[i];
+        pn *= beta;
+        a.p[i] = pn + a.r[i];
+    }
+}
+
+// x += alpha y ; r -= alpha v ; |r|^2
+__global__ void __launch_bounds__(256) vec_half1_kernel(VecArgs a)
+{
+    if (a.sc->done)
+        return;
+    const double alpha = a.sc->alpha;
+    double s[1] = {0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.len; i += (int64_t)gridDim.x * blockDim.x) {
+        a.x[i] += alpha * a.y[i];
+        const double rn = a.r[i] - alpha * a.v[i];
+        a.r[i] = rn;
+        s[0] += rn * rn;
+    }
+    grid_reduce<1>(s, a.rc, EPI_NORM1, a.sc, a.hist, nullptr);
+}
+
+// x += omega y ; r -= omega t ; |r|^2 ; (rt, r)
+__global__ void __launch_bounds__(256) vec_half2_kernel(VecArgs a)
+{
+    if (a.sc->done)
+        return;
+    const double omega = a.sc->omega;
+    double s[2] = {0.0, 0.0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.len; i += (int64_t)gridDim.x * blockDim.x) {
+        a.x[i] += omega * a.y[i];
+        const double rn = a.r[i] - omega * a.t[i];
+        a.r[i] = rn;
+        s[0] += rn * rn;
+        s[1] += a.rt[i] * rn;
+    }
+    grid_reduce<2>(s, a.rc, EPI_NORM2, a.sc, a.hist, nullptr);
+}
+
+// plain dot of two level-ordered vectors restricted to owner rows (ScalarProduct::dot)
+template <int B>
+__global__ void __launch_bounds__(256) dot_kernel(int64_t n, int64_t n_interior, const int* __restrict__ r2n,
+                                                  const double* __restrict__ x, const double* __restrict__ y,
+                                                  ReduceCtx rc, int epi, Scalars* sc, double* hist, double* out)
+{
+    double s[1] = {0.0};
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * B; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t q = t / B;
+        if (n_interior == n || r2n[q] < n_interior)
+            s[0] += x[t] * y[t];
+    }
+    grid_reduce<1>(s, rc, epi, sc, hist, out);
+}
+
+// y += a x
+__global__ void __launch_bounds__(256) axpy_kernel(int64_t len, double a, const double* __restrict__ x, double* __restrict__ y)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        y[i] += a * x[i];
+}
+
+__global__ void fill_kernel(double* p, int64_t len, double v)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+// halo: pack owner rows / scatter received ghost rows (positions in level order)
+template <int B>
+__global__ void gather_rows_kernel(int cnt, const int* __restrict__ rows, const double* __restrict__ v,
+                                   double* __restrict__ buf)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt * B; t += gridDim.x * blockDim.x)
+        buf[t] = v[(size_t)rows[t / B] * B + t % B];
+}
+template <int B>
+__global__ void scatter_rows_kernel(int cnt, const int* __restrict__ rows, const double* __restrict__ buf,
+                                    double* __restrict__ v)
+{
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt * B; t += gridDim.x * blockDim.x)
+        v[(size_t)rows[t / B] * B + t % B] = buf[t];
+}
+
+} // namespace opmb200

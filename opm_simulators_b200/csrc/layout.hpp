@@ -1,0 +1,78 @@
+// layout.hpp -- host-side analysis of a BCSR sparsity pattern into the device layout.
+//
+// Reference counterparts: Opm::getMatrixRowColoring (GraphColoring.hpp:246-307), the reorder maps
+// of MultithreadDILU (DILU.hpp:83-91), createReorderedMatrix / extractLowerAndUpperMatrices
+// (gpuistl/detail/coloringAndReorderingUtils.hpp:37-66) and the diagonal/transposed-entry index
+// searches the reference does per element on the device (DILUKernels.cu:207-268).  Here all of
+// it is integer work done once per sparsity pattern on the host.
+//
+// Device layout ("level-ordered SELL-32"):
+//   * rows are renumbered by (schedule level, natural index): position q <-> natural row r2n[q];
+//   * each level is cut into slices of <= 32 consecutive positions, one warp lane per row;
+//   * a slice owns wL + 1 + wU consecutive "slot rows" of 32 block slots each: its strictly-lower
+//     blocks (ascending natural column), its diagonal block, its strictly-upper blocks
+//     (descending natural column -- the order DILU.hpp:293 and convertToCRS traverse them);
+//     slot id g = slot_row*32 + lane;  value element e of slot g lives at
+//     (g & ~31)*b*b + e*32 + (g & 31)  => every warp-wide load is one contiguous 256-byte line;
+//   * slot_col[g] = POSITION of the column (-1: empty slot), slot_src[g] = index of the block in
+//     the caller's BCSR values (-1: empty, -2: identity block of a ghost row).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace opmb200 {
+
+constexpr int kSlice = 32;
+
+struct Layout {
+    int b = 0;
+    int64_t n = 0, n_interior = 0, nnzb = 0;
+    bool symmetric = true;
+
+    // reference-exact artefacts (what the parity tests compare bit for bit)
+    std::vector<int32_t> ref_level_rows, ref_level_ptr; // getMatrixRowColoring(A, LOWER)
+
+    // schedule (level sets of pattern(A) U pattern(A^T); identical to the above when symmetric)
+    int n_levels = 0;
+    std::vector<int32_t> level_q0; // [n_levels+1] first position of each level
+    std::vector<int32_t> r2n, n2r; // position <-> natural row
+
+    // slices
+    int n_slices = 0;
+    std::vector<int32_t> slice_q0;    // [n_slices+1]
+    std::vector<int32_t> slice_base;  // [n_slices+1] first slot row
+    std::vector<int32_t> slice_wl;    // [n_slices]
+    std::vector<int32_t> slice_wu;    // [n_slices]
+    std::vector<int32_t> slice_level; // [n_slices]
+    std::vector<int32_t> slice_lrank; // [n_slices+1] number of L slot rows before the slice
+    std::vector<int32_t> level_slice0; // [n_levels+1]
+    int64_t n_slot_rows = 0;
+
+    std::vector<int32_t> slot_col; // [n_slot_rows*32]
+    std::vector<int32_t> slot_src; // [n_slot_rows*32]
+    // DILU: for every L slot (compact L numbering) the slot of the transposed block, or -1
+    std::vector<int32_t> l_transpose; // [n_l_slot_rows*32]
+    // ILU0: per compact L slot, the (source slot in row j, destination slot in row i) update pairs
+    std::vector<int32_t> trip_ptr; // [n_l_slot_rows*32 + 1]
+    std::vector<int32_t> trip_src, trip_dst;
+
+    int64_t n_l_slot_rows() const { return slice_lrank.empty() ? 0 : slice_lrank.back(); }
+};
+
+// GraphColoring.hpp:246-307; type 0 SYMMETRIC, 1 LOWER, 2 UPPER.  Returns number of levels or a
+// negative opmb200_status.
+int row_coloring(int64_t n, const int32_t* rowptr, const int32_t* col, int type, int32_t* color,
+                 int32_t* level_rows, int32_t* level_ptr);
+
+// Builds everything above.  Returns 0 or an opmb200_status (diagonal missing, bad arguments).
+int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const int32_t* col, int64_t n_interior,
+                 bool want_ilu0, Layout& L, std::string& err);
+
+void partition_simple(int32_t num_cells, int32_t num_domains, int32_t* part);
+
+int localize(int64_t n_global, const int32_t* rowptr, const int32_t* col, const int32_t* part, int32_t rank,
+             int64_t* n_local, int64_t* n_interior, int64_t* nnzb_local, int32_t* out_l2g, int32_t* out_rowptr,
+             int32_t* out_col, int64_t* out_src);
+
+} // namespace opmb200

@@ -1,0 +1,1089 @@
+// solver.cu -- handle, kernel orchestration and the C ABI of include/opmb200.h.
+//
+// Host-side counterpart of Dune::FlexibleSolver + Dune::BiCGSTABSolver + the GPU back-end glue
+// (FlexibleSolver_impl.hpp:142-330, gpuistl/ISTLSolverGPUISTL.hpp:198-291).  The Krylov loop is
+// enqueued one iteration ahead of the device; all its scalars (rho, alpha, omega, norms, the
+// convergence verdict) live in device memory, so the host never waits for a dot product.
+#include "../../include/opmb200.h"
+#include "../../include/opmb200/property_tree.hpp"
+#include "kernels.cuh"
+#include "layout.hpp"
+
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace opmb200;
+
+namespace {
+thread_local std::string g_last_error;
+
+int fail(int code, const std::string& msg)
+{
+    g_last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                                                 \
+    do {                                                                                                               \
+        cudaError_t e__ = (expr);                                                                                      \
+        if (e__ != cudaSuccess)                                                                                        \
+            return fail(OPMB200_CUDA_ERROR,                                                                            \
+                        std::string("CUDA error ") + cudaGetErrorString(e__) + " in " #expr " at " __FILE__ ":"        \
+                            + std::to_string(__LINE__));                                                               \
+    } while (0)
+
+#define NCCL_TRY(expr)                                                                                                 \
+    do {                                                                                                               \
+        ncclResult_t e__ = (expr);                                                                                     \
+        if (e__ != ncclSuccess)                                                                                        \
+            return fail(OPMB200_NCCL_ERROR,                                                                            \
+                        std::string("NCCL error ") + ncclGetErrorString(e__) + " in " #expr " at " __FILE__ ":"        \
+                            + std::to_string(__LINE__));                                                               \
+    } while (0)
+
+#define TRY(expr)                                                                                                      \
+    do {                                                                                                               \
+        int rc__ = (expr);                                                                                             \
+        if (rc__ != OPMB200_SUCCESS)                                                                                   \
+            return rc__;                                                                                               \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        n = count;
+        return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+    }
+    cudaError_t upload(const std::vector<T>& h, cudaStream_t st)
+    {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty())
+            return e;
+        return cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+};
+
+bool is_device_ptr(const void* p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+enum PrecKind { PREC_NONE = 0, PREC_DILU = 1, PREC_ILU0 = 2 };
+
+double sentinel_host()
+{
+    const unsigned long long bits = kSentinelBits;
+    double d;
+    std::memcpy(&d, &bits, sizeof d);
+    return d;
+}
+} // namespace
+
+struct opmb200_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, size = 1;
+};
+
+struct opmb200_solver {
+    Layout L;
+    int b = 0;
+    int prec = PREC_ILU0;
+    double relaxation = 1.0;
+    double tol = 1e-2;
+    int maxiter = 200;
+    int verbosity = 0;
+    int op_repeats = 1;
+    int throttle = 3;
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_iter[2] = {nullptr, nullptr};
+    bool prepared = false;
+    int epoch = 0;
+
+    DevBuf<SliceMeta> slices;
+    DevBuf<int> slot_col, slot_src, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag;
+    DevBuf<double> A, F, dinv, vals_native;
+    DevBuf<double> vx, vr, vp, vv, vt, vy, vrt, vtmp, vw, nat0, nat1;
+    DevBuf<double> partials, hist, sums, dot_out;
+    DevBuf<unsigned int> counters; // [0] reduce arrivals, [1] ticket next, [2] ticket done
+    DevBuf<Scalars> sc;
+    Scalars* h_sc = nullptr; // pinned, two slots (double-buffered read-back)
+    double* h_small = nullptr;
+    int vec_grid = 0, max_grid = 0;
+
+    opmb200_comm* comm = nullptr;
+    int n_ranks = 1;
+    std::vector<int> nb_rank, send_ptr, recv_ptr;
+    DevBuf<int> send_rows, recv_rows; // positions
+    DevBuf<double> send_buf, recv_buf;
+
+    double t_analysis_s = 0, t_update_ms = 0, t_solve_ms = 0;
+    int64_t launches = 0;
+    std::vector<double> last_hist;
+
+    ~opmb200_solver()
+    {
+        if (h_sc)
+            cudaFreeHost(h_sc);
+        if (h_small)
+            cudaFreeHost(h_small);
+        for (cudaEvent_t e : {ev0, ev1, ev_iter[0], ev_iter[1]})
+            if (e)
+                cudaEventDestroy(e);
+        if (stream)
+            cudaStreamDestroy(stream);
+    }
+
+    int64_t len() const { return L.n * b; }
+    ReduceCtx rctx() { return ReduceCtx {partials.p, counters.p, max_grid, sums.p, n_ranks > 1 ? 1 : 0}; }
+    Ticket ticket() { return Ticket {counters.p + 1, counters.p + 2}; }
+    int slice_grid() const { return std::max(1, (L.n_slices + kWarpsPerCta - 1) / kWarpsPerCta); }
+};
+
+namespace {
+
+// ---- block-size dispatch ---------------------------------------------------------------------
+#define DISPATCH_B(bsz, ...)                                                                                           \
+    switch (bsz) {                                                                                                     \
+    case 1: { constexpr int B = 1; __VA_ARGS__; } break;                                                               \
+    case 2: { constexpr int B = 2; __VA_ARGS__; } break;                                                               \
+    case 3: { constexpr int B = 3; __VA_ARGS__; } break;                                                               \
+    default: { constexpr int B = 4; __VA_ARGS__; } break;                                                              \
+    }
+
+int check_launch(opmb200_solver* s, const char* what)
+{
+    ++s->launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return fail(OPMB200_CUDA_ERROR, std::string("kernel launch failed (") + what + "): " + cudaGetErrorString(e));
+    return OPMB200_SUCCESS;
+}
+
+// ---- halo exchange: OwnerOverlapCopyCommunication::copyOwnerToAll(v, v) over NCCL ----------------
+int copy_owner_to_all(opmb200_solver* s, double* v)
+{
+    if (s->n_ranks <= 1 || s->nb_rank.empty())
+        return OPMB200_SUCCESS;
+    const int b = s->b;
+    const int ns = s->send_ptr.back(), nr = s->recv_ptr.back();
+    if (ns > 0) {
+        DISPATCH_B(b, (gather_rows_kernel<B><<<std::min(1024, (ns * b + 255) / 256), 256, 0, s->stream>>>(
+                          ns, s->send_rows.p, v, s->send_buf.p)));
+        TRY(check_launch(s, "gather_rows"));
+    }
+    NCCL_TRY(ncclGroupStart());
+    for (size_t k = 0; k < s->nb_rank.size(); ++k) {
+        const int so = s->send_ptr[k], sn = s->send_ptr[k + 1] - so;
+        const int ro = s->recv_ptr[k], rn = s->recv_ptr[k + 1] - ro;
+        if (sn > 0)
+            NCCL_TRY(ncclSend(s->send_buf.p + (size_t)so * b, (size_t)sn * b, ncclDouble, s->nb_rank[k], s->comm->comm,
+                              s->stream));
+        if (rn > 0)
+            NCCL_TRY(ncclRecv(s->recv_buf.p + (size_t)ro * b, (size_t)rn * b, ncclDouble, s->nb_rank[k], s->comm->comm,
+                              s->stream));
+    }
+    NCCL_TRY(ncclGroupEnd());
+    if (nr > 0) {
+        DISPATCH_B(b, (scatter_rows_kernel<B><<<std::min(1024, (nr * b + 255) / 256), 256, 0, s->stream>>>(
+                          nr, s->recv_rows.p, s->recv_buf.p, v)));
+        TRY(check_launch(s, "scatter_rows"));
+    }
+    return OPMB200_SUCCESS;
+}
+
+// multi-rank tail of a fused reduction: all-reduce the local sums, then the scalar epilogue
+int finish_reduction(opmb200_solver* s, int nd, int epi, int check_done)
+{
+    if (s->n_ranks <= 1)
+        return OPMB200_SUCCESS;
+    NCCL_TRY(ncclAllReduce(s->sums.p, s->sums.p, nd, ncclDouble, ncclSum, s->comm->comm, s->stream));
+    epilogue_kernel<<<1, 1, 0, s->stream>>>(epi, s->sc.p, s->hist.p, s->sums.p, s->dot_out.p, check_done);
+    return check_launch(s, "epilogue");
+}
+
+// ---- SpMV --------------------------------------------------------------------------------------
+// mode 0: y = A x ; mode 1: y += alpha A x.   ndot/u/epi select the fused dots.
+int launch_spmv(opmb200_solver* s, const double* x, double* y, bool scaleadd, double alpha, int ndot, const double* u,
+                double* copy_out, int epi, int check_done)
+{
+    SpmvArgs a;
+    a.nslices = s->L.n_slices;
+    a.slices = s->slices.p;
+    a.slot_col = s->slot_col.p;
+    a.A = s->A.p;
+    a.r2n = s->r2n.p;
+    a.n = s->L.n;
+    a.n_interior = s->L.n_interior;
+    a.x = x;
+    a.y = y;
+    a.alpha = alpha;
+    a.u = u;
+    a.copy_out = copy_out;
+    a.rc = s->rctx();
+    a.epi = epi;
+    a.sc = s->sc.p;
+    a.hist = s->hist.p;
+    a.dot_out = s->dot_out.p;
+    a.check_done = check_done;
+    const int grid = s->slice_grid();
+#define SPMV_LAUNCH(SA, ND) spmv_kernel<B, SA, ND><<<grid, kCtaThreads, 0, s->stream>>>(a)
+    DISPATCH_B(s->b, {
+        if (scaleadd) {
+            if (ndot == 0) SPMV_LAUNCH(true, 0);
+            else if (ndot == 1) SPMV_LAUNCH(true, 1);
+            else SPMV_LAUNCH(true, 2);
+        } else {
+            if (ndot == 0) SPMV_LAUNCH(false, 0);
+            else if (ndot == 1) SPMV_LAUNCH(false, 1);
+            else SPMV_LAUNCH(false, 2);
+        }
+    });
+#undef SPMV_LAUNCH
+    TRY(check_launch(s, "spmv"));
+    if (ndot > 0)
+        TRY(finish_reduction(s, ndot, epi, check_done));
+    return OPMB200_SUCCESS;
+}
+
+// op.apply with the RepeatingOperator generalisation (tests/test_preconditionerfactory.cpp:231-276)
+int op_apply(opmb200_solver* s, const double* x, double* y, int ndot, const double* u, int epi, int check_done)
+{
+    if (s->op_repeats <= 1)
+        return launch_spmv(s, x, y, false, 0.0, ndot, u, nullptr, epi, check_done);
+    const double* src = x;
+    for (int r = 0; r < s->op_repeats; ++r) {
+        const bool last = (r == s->op_repeats - 1);
+        double* dst = last ? y : (r % 2 ? s->nat1.p : s->nat0.p);
+        TRY(launch_spmv(s, src, dst, false, 0.0, last ? ndot : 0, u, nullptr, epi, check_done));
+        src = dst;
+    }
+    return OPMB200_SUCCESS;
+}
+
+// ---- preconditioner ----------------------------------------------------------------------------
+SweepArgs sweep_args(opmb200_solver* s, const double* d, double* v, int ghost_zero, int check_done)
+{
+    SweepArgs a;
+    a.nslices = s->L.n_slices;
+    a.slices = s->slices.p;
+    a.slot_col = s->slot_col.p;
+    a.M = s->prec == PREC_ILU0 ? s->F.p : s->A.p;
+    a.dinv = s->dinv.p;
+    a.d = d;
+    a.tmp = s->vtmp.p;
+    a.v = v;
+    a.level_q0 = s->level_q0.p;
+    a.n_levels = s->L.n_levels;
+    a.throttle = s->throttle;
+    a.relax = (std::abs(s->relaxation - 1.0) > 1e-15) ? s->relaxation : 1.0;
+    a.r2n = s->r2n.p;
+    a.n = s->L.n;
+    a.n_interior = s->L.n_interior;
+    a.ghost_zero = ghost_zero;
+    a.ticket = s->ticket();
+    a.sc = s->sc.p;
+    a.check_done = check_done;
+    return a;
+}
+
+int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
+{
+    const int grid = s->slice_grid();
+    DISPATCH_B(s->b, {
+        if (s->prec == PREC_ILU0) {
+            if (upper) sweep_kernel<B, true, true><<<grid, kCtaThreads, 0, s->stream>>>(a);
+            else sweep_kernel<B, true, false><<<grid, kCtaThreads, 0, s->stream>>>(a);
+        } else {
+            if (upper) sweep_kernel<B, false, true><<<grid, kCtaThreads, 0, s->stream>>>(a);
+            else sweep_kernel<B, false, false><<<grid, kCtaThreads, 0, s->stream>>>(a);
+        }
+    });
+    return check_launch(s, upper ? "upper sweep" : "lower sweep");
+}
+
+// Preconditioner::apply(v, d) on level-ordered device vectors, incl. BlockPreconditioner's halo copy
+int prec_apply(opmb200_solver* s, const double* d, double* v, int ghost_zero, int check_done)
+{
+    if (s->prec == PREC_NONE) {
+        CUDA_TRY(cudaMemcpyAsync(v, d, s->len() * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        return OPMB200_SUCCESS;
+    }
+    const SweepArgs a = sweep_args(s, d, v, ghost_zero, check_done);
+    TRY(launch_sweep(s, a, false));
+    TRY(launch_sweep(s, a, true));
+    return copy_owner_to_all(s, v);
+}
+
+int prec_update(opmb200_solver* s)
+{
+    if (s->prec == PREC_NONE)
+        return OPMB200_SUCCESS;
+    ++s->epoch;
+    FactorArgs a;
+    a.nslices = s->L.n_slices;
+    a.slices = s->slices.p;
+    a.slot_col = s->slot_col.p;
+    a.A = s->A.p;
+    a.F = s->F.p;
+    a.l_transpose = s->l_transpose.p;
+    a.trip_ptr = s->trip_ptr.p;
+    a.trip_src = s->trip_src.p;
+    a.trip_dst = s->trip_dst.p;
+    a.dinv = s->dinv.p;
+    a.row_flag = s->row_flag.p;
+    a.epoch = s->epoch;
+    a.ticket = s->ticket();
+    a.sc = s->sc.p;
+    const int grid = s->slice_grid();
+    DISPATCH_B(s->b, {
+        if (s->prec == PREC_ILU0) ilu0_factor_kernel<B><<<grid, kCtaThreads, 0, s->stream>>>(a);
+        else dilu_factor_kernel<B><<<grid, kCtaThreads, 0, s->stream>>>(a);
+    });
+    return check_launch(s, "factorisation");
+}
+
+int relayout(opmb200_solver* s, const double* dev_vals)
+{
+    const int64_t nslots = s->L.n_slot_rows * kSlice;
+    const int grid = (int)std::min<int64_t>((nslots + 255) / 256, (int64_t)s->num_sms * 16);
+    DISPATCH_B(s->b, (relayout_kernel<B><<<std::max(grid, 1), 256, 0, s->stream>>>(
+                      nslots, s->slot_src.p, dev_vals, s->A.p, s->prec == PREC_ILU0 ? s->F.p : nullptr)));
+    return check_launch(s, "relayout");
+}
+
+// ---- staging helpers: caller vector (host or device, natural order) <-> level-ordered device vector
+int stage_in(opmb200_solver* s, const double* user, double* nat_tmp, double* lvl)
+{
+    const double* src = user;
+    if (!is_device_ptr(user)) {
+        CUDA_TRY(cudaMemcpyAsync(nat_tmp, user, s->len() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        src = nat_tmp;
+    }
+    DISPATCH_B(s->b, (permute_in_kernel<B><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, s->r2n.p, src, lvl)));
+    return check_launch(s, "permute_in");
+}
+
+int stage_out(opmb200_solver* s, const double* lvl, double* nat_tmp, double* user)
+{
+    const bool dev = is_device_ptr(user);
+    double* dst = dev ? user : nat_tmp;
+    DISPATCH_B(s->b, (permute_out_kernel<B><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, s->n2r.p, lvl, dst)));
+    TRY(check_launch(s, "permute_out"));
+    if (!dev)
+        CUDA_TRY(cudaMemcpyAsync(user, nat_tmp, s->len() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    return OPMB200_SUCCESS;
+}
+
+int parse_options(opmb200_solver* s, const char* json)
+{
+    PropertyTree prm;
+    if (json && *json) {
+        try {
+            prm = PropertyTree::fromJson(json);
+        } catch (const std::exception& e) {
+            return fail(OPMB200_BAD_OPTIONS, e.what());
+        }
+    }
+    try {
+        // FlexibleSolver::initSolver (FlexibleSolver_impl.hpp:195-330)
+        s->tol = prm.get<double>("tol", 1e-2);
+        s->maxiter = prm.get<int>("maxiter", 200);
+        s->verbosity = prm.get<int>("verbosity", 0);
+        const std::string solver = prm.get<std::string>("solver", "bicgstab");
+        if (solver != "bicgstab" && solver != "gpubicgstab" && solver != "b200bicgstab")
+            return fail(OPMB200_BAD_OPTIONS, "Properties: Solver " + solver + " not known.");
+        // PreconditionerFactory::doCreate (PreconditionerFactory_impl.hpp:86-106)
+        std::string type = prm.get<std::string>("preconditioner.type", "paroverilu0");
+        std::transform(type.begin(), type.end(), type.begin(), ::tolower);
+        if (type == "dilu" || type == "gpudilu" || type == "b200dilu")
+            s->prec = PREC_DILU;
+        else if (type == "ilu0" || type == "paroverilu0" || type == "opmilu0" || type == "opmgpuilu0" || type == "gpuilu0"
+                 || type == "b200ilu0" || type == "ilun")
+            s->prec = PREC_ILU0;
+        else if (type == "nothing" || type == "none")
+            s->prec = PREC_NONE; // the identity preconditioner the reference's tests register by hand
+        else
+            return fail(OPMB200_BAD_OPTIONS,
+                        "Preconditioner type " + type
+                            + " is not registered in the factory. Available types are: dilu ilu0 paroverilu0 ilun "
+                              "opmilu0 opmgpuilu0 gpuilu0 gpudilu nothing");
+        if (prm.get<int>("preconditioner.ilulevel", 0) != 0)
+            return fail(OPMB200_BAD_OPTIONS, "preconditioner.ilulevel > 0 (ILU(n)) is outside this path");
+        if (prm.get<int>("preconditioner.mixed_precision_scheme", 0) != 0)
+            return fail(OPMB200_BAD_OPTIONS, "preconditioner.mixed_precision_scheme != 0 is outside this path");
+        s->relaxation = prm.get<double>("preconditioner.relaxation", 1.0);
+        s->op_repeats = prm.get<int>("b200.operator_repeats", 1);
+        s->throttle = prm.get<int>("b200.throttle_levels", 3);
+    } catch (const std::exception& e) {
+        return fail(OPMB200_BAD_OPTIONS, e.what());
+    }
+    return OPMB200_SUCCESS;
+}
+
+int init_scalars(opmb200_solver* s, double reduction)
+{
+    Scalars& h = s->h_sc[0];
+    std::memset(&h, 0, sizeof(Scalars));
+    h.rho = h.alpha = h.omega = 1.0;
+    h.reduction = reduction;
+    h.maxiter = s->maxiter;
+    h.hist_cap = (int)s->hist.n;
+    CUDA_TRY(cudaMemcpyAsync(s->sc.p, &h, sizeof(Scalars), cudaMemcpyHostToDevice, s->stream));
+    return OPMB200_SUCCESS;
+}
+
+VecArgs vec_args(opmb200_solver* s)
+{
+    VecArgs a;
+    a.len = s->len();
+    a.x = s->vx.p;
+    a.r = s->vr.p;
+    a.p = s->vp.p;
+    a.v = s->vv.p;
+    a.t = s->vt.p;
+    a.y = s->vy.p;
+    a.rt = s->vrt.p;
+    a.rc = s->rctx();
+    a.sc = s->sc.p;
+    a.hist = s->hist.p;
+    return a;
+}
+
+// one BiCGSTAB iteration (two half steps) enqueued on the stream
+int enqueue_iteration(opmb200_solver* s)
+{
+    const VecArgs va = vec_args(s);
+    const int gz = 1; // Dune: y = 0 before every preconditioner application
+    vec_p_update_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);
+    TRY(check_launch(s, "vec_p_update"));
+    TRY(prec_apply(s, s->vp.p, s->vy.p, gz, 1));                       // y = W^-1 p
+    TRY(op_apply(s, s->vy.p, s->vv.p, 1, s->vrt.p, EPI_H, 1));          // v = A y ; h = (rt, v)
+    vec_half1_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);          // x += alpha y ; r -= alpha v ; |r|
+    TRY(check_launch(s, "vec_half1"));
+    TRY(finish_reduction(s, 1, EPI_NORM1, 1));
+    TRY(prec_apply(s, s->vr.p, s->vy.p, gz, 1));                       // y = W^-1 r
+    TRY(op_apply(s, s->vy.p, s->vt.p, 2, s->vr.p, EPI_OMEGA, 1));       // t = A y ; (t,r), (t,t)
+    vec_half2_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);          // x += omega y ; r -= omega t ; |r| ; (rt,r)
+    TRY(check_launch(s, "vec_half2"));
+    TRY(finish_reduction(s, 2, EPI_NORM2, 1));
+    return OPMB200_SUCCESS;
+}
+
+int do_solve(opmb200_solver* s, double* x, double* b, double reduction, opmb200_result* res)
+{
+    const auto t0 = std::chrono::steady_clock::now();
+    if (reduction < 0)
+        reduction = s->tol;
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    TRY(stage_in(s, x, s->nat0.p, s->vx.p));
+    TRY(stage_in(s, b, s->nat1.p, s->vr.p));
+    TRY(init_scalars(s, reduction));
+    const size_t bytes = s->len() * sizeof(double);
+    // _prec->pre(x, r): BlockPreconditioner makes x consistent on the ghosts
+    TRY(copy_owner_to_all(s, s->vx.p));
+    CUDA_TRY(cudaMemsetAsync(s->vp.p, 0, bytes, s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->vv.p, 0, bytes, s->stream));
+    // r = b - A x ; rt = r ; norm0 = |r|
+    if (s->op_repeats <= 1) {
+        TRY(launch_spmv(s, s->vx.p, s->vr.p, true, -1.0, 1, nullptr, s->vrt.p, EPI_INIT, 0));
+    } else {
+        // RepeatingOperator::applyscaleadd: temp = A^k x ; temp *= alpha ; r += temp
+        TRY(op_apply(s, s->vx.p, s->vw.p, 0, nullptr, EPI_NONE, 0));
+        axpy_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->len(), -1.0, s->vw.p, s->vr.p);
+        TRY(check_launch(s, "axpy(init)"));
+        CUDA_TRY(cudaMemcpyAsync(s->vrt.p, s->vr.p, bytes, cudaMemcpyDeviceToDevice, s->stream));
+        DISPATCH_B(s->b, (dot_kernel<B><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, s->L.n_interior, s->r2n.p, s->vr.p,
+                                                                         s->vr.p, s->rctx(), EPI_INIT, s->sc.p,
+                                                                         s->hist.p, s->dot_out.p)));
+        TRY(check_launch(s, "dot(init)"));
+        TRY(finish_reduction(s, 1, EPI_INIT, 0));
+    }
+
+    // ---- iterate, one iteration enqueued ahead of the read-back ------------------------------------
+    CUDA_TRY(cudaMemcpyAsync(&s->h_sc[1], s->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev_iter[1], s->stream));
+    int enq = 0, slot = 1; // `slot` = pinned slot holding the most recent read-back in flight
+    Scalars fin;
+    while (true) {
+        const bool can_enqueue = enq < s->maxiter;
+        if (can_enqueue) {
+            TRY(enqueue_iteration(s));
+            ++enq;
+            const int ns = slot ^ 1;
+            CUDA_TRY(cudaMemcpyAsync(&s->h_sc[ns], s->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaEventRecord(s->ev_iter[ns], s->stream));
+        }
+        // wait for the state BEFORE the iteration just enqueued
+        CUDA_TRY(cudaEventSynchronize(s->ev_iter[slot]));
+        fin = s->h_sc[slot];
+        if (fin.done || !can_enqueue)
+            break;
+        slot ^= 1;
+    }
+    if (!fin.done) { // ran out of enqueued iterations without the device noticing (cannot happen)
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        fin = s->h_sc[slot];
+    }
+    TRY(stage_out(s, s->vx.p, s->nat0.p, x));
+    TRY(stage_out(s, s->vr.p, s->nat1.p, b));
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->t_solve_ms = ms;
+    // final state (the early-exit kernels leave it untouched once done is set)
+    CUDA_TRY(cudaMemcpy(&fin, s->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost));
+    s->last_hist.assign(std::max(fin.hist_count, 0), 0.0);
+    if (fin.hist_count > 0)
+        CUDA_TRY(cudaMemcpy(s->last_hist.data(), s->hist.p, sizeof(double) * fin.hist_count, cudaMemcpyDeviceToHost));
+    if (res) {
+        // IterativeSolver::Iteration::_finalize
+        res->iterations = (int)fin.it;
+        res->reduction = fin.norm0 > 0 ? fin.norm / fin.norm0 : 0.0;
+        res->converged = fin.converged;
+        res->conv_rate = fin.it > 0 ? std::pow(res->reduction, 1.0 / fin.it) : 0.0;
+        res->elapsed = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+    if (s->verbosity > 1 && (!s->comm || s->comm->rank == 0)) {
+        std::printf("=== opmb200 BiCGSTABSolver\n Iter          Defect            Rate\n");
+        for (size_t i = 0; i < s->last_hist.size(); ++i)
+            std::printf("%5.1f %16.8e %16.8e\n", 0.5 * i, s->last_hist[i],
+                        i ? s->last_hist[i] / s->last_hist[i - 1] : 0.0);
+    }
+    if (fin.abort_code == 1)
+        return fail(OPMB200_SOLVER_ABORT, "breakdown in BiCGSTAB (rho, omega or h <= EPSILON) after "
+                                              + std::to_string(fin.it) + " iterations");
+    if (fin.abort_code == 2)
+        return fail(OPMB200_SOLVER_ABORT, "BiCGSTABSolver: defect is infinite or NaN");
+    return OPMB200_SUCCESS;
+}
+
+} // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int opmb200_version(void) { return OPMB200_VERSION; }
+const char* opmb200_last_error(void) { return g_last_error.c_str(); }
+
+int opmb200_device_count(int* count)
+{
+    if (!count)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    *count = 0;
+    CUDA_TRY(cudaGetDeviceCount(count));
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_set_device(int device)
+{
+    CUDA_TRY(cudaSetDevice(device));
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_row_coloring(int64_t n, const int32_t* rowptr, const int32_t* colidx, int type, int32_t* color,
+                         int32_t* level_rows, int32_t* level_ptr, int32_t* n_levels)
+{
+    if (!rowptr || !color || !level_rows || !level_ptr || !n_levels || n < 0)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    const int nl = row_coloring(n, rowptr, colidx, type, color, level_rows, level_ptr);
+    if (nl < 0)
+        return fail(-nl, nl == -OPMB200_DIAGONAL_MISSING ? "diagonal entry missing" : "bad colouring type");
+    *n_levels = nl;
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_partition_simple(int32_t num_cells, int32_t num_domains, int32_t* part)
+{
+    if (!part || num_cells < 0 || num_domains <= 0)
+        return fail(OPMB200_INVALID_ARGUMENT, "bad partition arguments");
+    partition_simple(num_cells, num_domains, part);
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_localize(int64_t n_global, const int32_t* rowptr, const int32_t* colidx, const int32_t* part, int32_t rank,
+                     int64_t* n_local, int64_t* n_interior, int64_t* nnzb_local, int32_t* out_l2g, int32_t* out_rowptr,
+                     int32_t* out_colidx, int64_t* out_src)
+{
+    if (!rowptr || !colidx || !part || !n_local || !n_interior || !nnzb_local)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (out_l2g && (!out_rowptr || !out_colidx || !out_src))
+        return fail(OPMB200_INVALID_ARGUMENT, "null output buffer");
+    return localize(n_global, rowptr, colidx, part, rank, n_local, n_interior, nnzb_local, out_l2g, out_rowptr,
+                    out_colidx, out_src);
+}
+
+int opmb200_comm_unique_id(void* id128)
+{
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (!id128)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    NCCL_TRY(ncclGetUniqueId(reinterpret_cast<ncclUniqueId*>(id128)));
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_comm_create(int rank, int n_ranks, const void* id128, opmb200_comm** out)
+{
+    if (!id128 || !out || rank < 0 || rank >= n_ranks)
+        return fail(OPMB200_INVALID_ARGUMENT, "bad communicator arguments");
+    ncclUniqueId id;
+    std::memcpy(&id, id128, sizeof id);
+    auto* c = new opmb200_comm;
+    c->rank = rank;
+    c->size = n_ranks;
+    ncclResult_t e = ncclCommInitRank(&c->comm, n_ranks, id, rank);
+    if (e != ncclSuccess) {
+        delete c;
+        return fail(OPMB200_NCCL_ERROR, std::string("ncclCommInitRank: ") + ncclGetErrorString(e));
+    }
+    *out = c;
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_comm_destroy(opmb200_comm* c)
+{
+    if (!c)
+        return OPMB200_SUCCESS;
+    if (c->comm)
+        ncclCommDestroy(c->comm);
+    delete c;
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int64_t nnzb, const int32_t* rowptr,
+                   const int32_t* colidx, int64_t n_interior, opmb200_comm* comm, const opmb200_halo* halo,
+                   opmb200_solver** out)
+{
+    if (!out)
+        return fail(OPMB200_INVALID_ARGUMENT, "null output handle");
+    *out = nullptr;
+    auto s = std::make_unique<opmb200_solver>();
+    TRY(parse_options(s.get(), json_options));
+    const auto t0 = std::chrono::steady_clock::now();
+    std::string err;
+    const int rc = build_layout(block_size, n_rows, nnzb, rowptr, colidx, n_interior, s->prec == PREC_ILU0, s->L, err);
+    if (rc != OPMB200_SUCCESS)
+        return fail(rc, err);
+    s->t_analysis_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    s->b = block_size;
+    s->comm = comm;
+    s->n_ranks = comm ? comm->size : 1;
+    if (s->n_ranks > 1 && !halo)
+        return fail(OPMB200_INVALID_ARGUMENT, "a communicator needs a halo description");
+
+    // ---- device ----------------------------------------------------------------------------------
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(OPMB200_CUDA_ERROR, "no CUDA device: libopmb200 has no CPU fallback");
+    }
+    CUDA_TRY(cudaGetDevice(&s->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
+    s->num_sms = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&s->ev0));
+    CUDA_TRY(cudaEventCreate(&s->ev1));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_iter[0], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&s->ev_iter[1], cudaEventDisableTiming));
+    CUDA_TRY(cudaMallocHost((void**)&s->h_sc, 2 * sizeof(Scalars)));
+    CUDA_TRY(cudaMallocHost((void**)&s->h_small, 16 * sizeof(double)));
+
+    const Layout& L = s->L;
+    const int BB = block_size * block_size;
+    cudaStream_t st = s->stream;
+    std::vector<SliceMeta> meta(L.n_slices);
+    for (int i = 0; i < L.n_slices; ++i)
+        meta[i] = SliceMeta {L.slice_q0[i], L.slice_q0[i + 1] - L.slice_q0[i], L.slice_base[i], L.slice_wl[i],
+                             L.slice_wu[i], L.slice_level[i], L.slice_lrank[i], 0};
+    CUDA_TRY(s->slices.upload(meta, st));
+    CUDA_TRY(s->slot_col.upload(L.slot_col, st));
+    CUDA_TRY(s->slot_src.upload(L.slot_src, st));
+    CUDA_TRY(s->r2n.upload(L.r2n, st));
+    CUDA_TRY(s->n2r.upload(L.n2r, st));
+    CUDA_TRY(s->level_q0.upload(L.level_q0, st));
+    CUDA_TRY(s->l_transpose.upload(L.l_transpose, st));
+    if (s->prec == PREC_ILU0) {
+        CUDA_TRY(s->trip_ptr.upload(L.trip_ptr, st));
+        CUDA_TRY(s->trip_src.upload(L.trip_src, st));
+        CUDA_TRY(s->trip_dst.upload(L.trip_dst, st));
+        CUDA_TRY(s->F.alloc((size_t)L.n_slot_rows * kSlice * BB));
+    }
+    CUDA_TRY(s->A.alloc((size_t)L.n_slot_rows * kSlice * BB));
+    CUDA_TRY(s->dinv.alloc((size_t)L.n * BB));
+    CUDA_TRY(s->row_flag.alloc((size_t)L.n));
+    CUDA_TRY(cudaMemsetAsync(s->row_flag.p, 0, std::max<size_t>(L.n, 1) * sizeof(int), st));
+    CUDA_TRY(s->vals_native.alloc((size_t)nnzb * BB));
+    const size_t len = (size_t)L.n * block_size;
+    for (DevBuf<double>* v : {&s->vx, &s->vr, &s->vp, &s->vv, &s->vt, &s->vy, &s->vrt, &s->vtmp, &s->vw, &s->nat0, &s->nat1}) {
+        CUDA_TRY(v->alloc(len));
+        CUDA_TRY(cudaMemsetAsync(v->p, 0, std::max<size_t>(len, 1) * sizeof(double), st));
+    }
+    s->vec_grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)s->num_sms * 8, ((int64_t)len + 255) / 256));
+    s->max_grid = std::max(s->vec_grid, s->slice_grid());
+    CUDA_TRY(s->partials.alloc((size_t)2 * s->max_grid));
+    CUDA_TRY(s->hist.alloc((size_t)2 * s->maxiter + 4));
+    CUDA_TRY(s->sums.alloc(4));
+    CUDA_TRY(s->dot_out.alloc(4));
+    CUDA_TRY(s->counters.alloc(4));
+    CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, 4 * sizeof(unsigned int), st));
+    CUDA_TRY(s->sc.alloc(1));
+    CUDA_TRY(cudaMemsetAsync(s->sc.p, 0, sizeof(Scalars), st));
+    // the sweeps' intermediate vector is all-sentinel between applies
+    fill_kernel<<<s->vec_grid, 256, 0, st>>>(s->vtmp.p, (int64_t)len, sentinel_host());
+    TRY(check_launch(s.get(), "fill"));
+
+    // ---- halo lists -> positions --------------------------------------------------------------------
+    if (s->n_ranks > 1) {
+        const int nn = halo->n_neighbors;
+        s->nb_rank.assign(halo->neighbor_rank, halo->neighbor_rank + nn);
+        s->send_ptr.assign(halo->send_ptr, halo->send_ptr + nn + 1);
+        s->recv_ptr.assign(halo->recv_ptr, halo->recv_ptr + nn + 1);
+        std::vector<int> sp(s->send_ptr.back()), rp(s->recv_ptr.back());
+        for (size_t i = 0; i < sp.size(); ++i) {
+            const int r = halo->send_rows[i];
+            if (r < 0 || r >= n_interior)
+                return fail(OPMB200_INVALID_ARGUMENT, "halo send row is not an owner row");
+            sp[i] = L.n2r[r];
+        }
+        for (size_t i = 0; i < rp.size(); ++i) {
+            const int r = halo->recv_rows[i];
+            if (r < n_interior || r >= n_rows)
+                return fail(OPMB200_INVALID_ARGUMENT, "halo recv row is not a ghost row");
+            rp[i] = L.n2r[r];
+        }
+        CUDA_TRY(s->send_rows.upload(sp, st));
+        CUDA_TRY(s->recv_rows.upload(rp, st));
+        CUDA_TRY(s->send_buf.alloc(sp.size() * block_size));
+        CUDA_TRY(s->recv_buf.alloc(rp.size() * block_size));
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    *out = s.release();
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_destroy(opmb200_solver* s)
+{
+    if (s) {
+        cudaStreamSynchronize(s->stream);
+        delete s;
+    }
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_update_values(opmb200_solver* s, const double* values)
+{
+    if (!s || !values)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    const double* dev = values;
+    if (!is_device_ptr(values)) {
+        CUDA_TRY(cudaMemcpyAsync(s->vals_native.p, values, s->vals_native.n * sizeof(double), cudaMemcpyHostToDevice,
+                                 s->stream));
+        dev = s->vals_native.p;
+    }
+    TRY(relayout(s, dev));
+    TRY(prec_update(s));
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    int* h_err = reinterpret_cast<int*>(s->h_small);
+    CUDA_TRY(cudaMemcpyAsync(h_err, &s->sc.p->factor_error, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    s->t_update_ms = ms;
+    int bad = *h_err;
+    if (s->n_ranks > 1) { // all ranks fail together (comm.min vote, ParallelOverlappingILU0_impl.hpp:598-606)
+        int* d_flag = reinterpret_cast<int*>(s->sums.p);
+        CUDA_TRY(cudaMemcpyAsync(d_flag, &bad, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        NCCL_TRY(ncclAllReduce(d_flag, d_flag, 1, ncclInt, ncclMax, s->comm->comm, s->stream));
+        CUDA_TRY(cudaMemcpyAsync(h_err, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        bad = *h_err;
+    }
+    if (bad) {
+        CUDA_TRY(cudaMemsetAsync(&s->sc.p->factor_error, 0, sizeof(int), s->stream));
+        s->prepared = false;
+        return fail(OPMB200_MATRIX_BLOCK_ERROR, "Singular matrix block");
+    }
+    s->prepared = true;
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_precond_apply(opmb200_solver* s, double* v, const double* d)
+{
+    if (!s || !v || !d)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (!s->prepared)
+        return fail(OPMB200_NOT_PREPARED, "update_values has not been called");
+    TRY(stage_in(s, d, s->nat0.p, s->vp.p));
+    TRY(stage_in(s, v, s->nat1.p, s->vy.p)); // ILU0 leaves ghost entries of v as they were
+    TRY(prec_apply(s, s->vp.p, s->vy.p, 0, 0));
+    TRY(stage_out(s, s->vy.p, s->nat0.p, v));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_op_apply(opmb200_solver* s, const double* x, double* y)
+{
+    if (!s || !x || !y)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (!s->prepared)
+        return fail(OPMB200_NOT_PREPARED, "update_values has not been called");
+    TRY(stage_in(s, x, s->nat0.p, s->vp.p));
+    TRY(launch_spmv(s, s->vp.p, s->vy.p, false, 0.0, 0, nullptr, nullptr, EPI_NONE, 0));
+    TRY(stage_out(s, s->vy.p, s->nat0.p, y));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_op_applyscaleadd(opmb200_solver* s, double alpha, const double* x, double* y)
+{
+    if (!s || !x || !y)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (!s->prepared)
+        return fail(OPMB200_NOT_PREPARED, "update_values has not been called");
+    TRY(stage_in(s, x, s->nat0.p, s->vp.p));
+    TRY(stage_in(s, y, s->nat1.p, s->vy.p));
+    TRY(launch_spmv(s, s->vp.p, s->vy.p, true, alpha, 0, nullptr, nullptr, EPI_NONE, 0));
+    TRY(stage_out(s, s->vy.p, s->nat0.p, y));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_dot(opmb200_solver* s, const double* x, const double* y, double* result)
+{
+    if (!s || !x || !y || !result)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    TRY(stage_in(s, x, s->nat0.p, s->vp.p));
+    TRY(stage_in(s, y, s->nat1.p, s->vy.p));
+    DISPATCH_B(s->b, (dot_kernel<B><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, s->L.n_interior, s->r2n.p, s->vp.p, s->vy.p,
+                                                                     s->rctx(), EPI_DOT, s->sc.p, s->hist.p,
+                                                                     s->dot_out.p)));
+    TRY(check_launch(s, "dot"));
+    TRY(finish_reduction(s, 1, EPI_DOT, 0));
+    CUDA_TRY(cudaMemcpyAsync(s->h_small, s->dot_out.p, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    *result = s->h_small[0];
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_solve(opmb200_solver* s, double* x, double* b, double reduction, opmb200_result* res)
+{
+    if (!s || !x || !b)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (!s->prepared)
+        return fail(OPMB200_NOT_PREPARED, "update_values has not been called");
+    return do_solve(s, x, b, reduction, res);
+}
+
+int opmb200_get_info(opmb200_solver* s, opmb200_info* info)
+{
+    if (!s || !info)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    info->block_size = s->b;
+    info->n_rows = s->L.n;
+    info->n_interior = s->L.n_interior;
+    info->nnzb = s->L.nnzb;
+    info->n_levels = (int)s->L.ref_level_ptr.size() - 1;
+    info->n_slices = s->L.n_slices;
+    info->padded_blocks = s->L.n_slot_rows * kSlice;
+    info->structurally_symmetric = s->L.symmetric;
+    info->preconditioner = s->prec;
+    info->relaxation = s->relaxation;
+    info->tol = s->tol;
+    info->maxiter = s->maxiter;
+    info->n_ranks = s->n_ranks;
+    info->t_analysis_s = s->t_analysis_s;
+    info->t_update_ms = s->t_update_ms;
+    info->t_solve_ms = s->t_solve_ms;
+    info->kernel_launches = s->launches;
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_get_levels(opmb200_solver* s, int32_t* level_ptr, int32_t* level_rows)
+{
+    if (!s)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (level_ptr)
+        std::copy(s->L.ref_level_ptr.begin(), s->L.ref_level_ptr.end(), level_ptr);
+    if (level_rows)
+        std::copy(s->L.ref_level_rows.begin(), s->L.ref_level_rows.end(), level_rows);
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_get_reorder(opmb200_solver* s, int32_t* reordered_to_natural, int32_t* natural_to_reordered)
+{
+    if (!s)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    // DILU.hpp:83-91: walk the level sets in order
+    for (int64_t k = 0; k < s->L.n; ++k) {
+        const int32_t j = s->L.ref_level_rows[k];
+        if (reordered_to_natural)
+            reordered_to_natural[k] = j;
+        if (natural_to_reordered)
+            natural_to_reordered[j] = (int32_t)k;
+    }
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_get_dinv(opmb200_solver* s, double* dinv)
+{
+    if (!s || !dinv)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (!s->prepared || s->prec == PREC_NONE)
+        return fail(OPMB200_NOT_PREPARED, "no factorisation available");
+    const int BB = s->b * s->b;
+    std::vector<double> h((size_t)s->L.n * BB);
+    CUDA_TRY(cudaMemcpy(h.data(), s->dinv.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int64_t q = 0; q < s->L.n; ++q)
+        std::memcpy(dinv + (size_t)s->L.r2n[q] * BB, h.data() + (size_t)q * BB, sizeof(double) * BB);
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_get_ilu0(opmb200_solver* s, double* lu)
+{
+    if (!s || !lu)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (!s->prepared || s->prec != PREC_ILU0)
+        return fail(OPMB200_NOT_PREPARED, "no ILU0 factorisation available");
+    const int BB = s->b * s->b;
+    std::vector<double> h(s->F.n);
+    CUDA_TRY(cudaMemcpy(h.data(), s->F.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    const int64_t nslots = s->L.n_slot_rows * kSlice;
+    for (int64_t g = 0; g < nslots; ++g) {
+        const int src = s->L.slot_src[g];
+        if (src < 0)
+            continue;
+        for (int e = 0; e < BB; ++e)
+            lu[(size_t)src * BB + e] = h[(size_t)(g & ~(int64_t)31) * BB + (size_t)e * 32 + (g & 31)];
+    }
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_get_history(opmb200_solver* s, double* hist, int capacity, int* count)
+{
+    if (!s || !count)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    *count = (int)s->last_hist.size();
+    if (hist)
+        std::copy_n(s->last_hist.begin(), std::min<size_t>(capacity, s->last_hist.size()), hist);
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, double* ms_per_launch, double* algorithmic_bytes)
+{
+    if (!s || !ms_per_launch || reps <= 0)
+        return fail(OPMB200_INVALID_ARGUMENT, "bad arguments");
+    if (!s->prepared)
+        return fail(OPMB200_NOT_PREPARED, "update_values has not been called");
+    const double N = (double)s->L.n, nnzb = (double)s->L.nnzb, b = s->b;
+    const double blk = 8 * b * b + 4;
+    double bytes = 0;
+    // benign scalar state for the vector kernels
+    Scalars h;
+    std::memset(&h, 0, sizeof h);
+    h.alpha = h.omega = 1e-3;
+    h.beta = 0.5;
+    h.norm0 = 1;
+    h.maxiter = 1 << 30;
+    h.reduction = 0;
+    CUDA_TRY(cudaMemcpyAsync(s->sc.p, &h, sizeof h, cudaMemcpyHostToDevice, s->stream));
+    const VecArgs va = vec_args(s);
+    if (what == 4 || what == 5) {
+        // one sweep of the (lower, upper) pair: the pair must run together (sentinel protocol),
+        // so bracket the wanted half with events inside every repetition and add the times up
+        const SweepArgs sa = sweep_args(s, s->vr.p, s->vy.p, 1, 0);
+        if (s->prec == PREC_NONE)
+            return fail(OPMB200_INVALID_ARGUMENT, "no preconditioner to time");
+        cudaEvent_t em;
+        CUDA_TRY(cudaEventCreate(&em));
+        double total = 0;
+        for (int it = 0; it < warmup + reps; ++it) {
+            CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+            TRY(launch_sweep(s, sa, false));
+            CUDA_TRY(cudaEventRecord(em, s->stream));
+            TRY(launch_sweep(s, sa, true));
+            CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, what == 4 ? s->ev0 : em, what == 4 ? em : s->ev1));
+            if (it >= warmup)
+                total += ms;
+        }
+        cudaEventDestroy(em);
+        *ms_per_launch = total / reps;
+        if (algorithmic_bytes)
+            *algorithmic_bytes = 0.5 * (s->prec == PREC_ILU0 ? nnzb * blk + 32 * b * N + 16 * (N + 1) + 8 * N
+                                                             : (nnzb - N) * blk + 16 * b * b * N + 40 * b * N
+                                                                   + 16 * (N + 1) + 8 * N);
+        return OPMB200_SUCCESS;
+    }
+    for (int it = 0; it < warmup + reps; ++it) {
+        if (it == warmup)
+            CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+        switch (what) {
+        case 0:
+            TRY(launch_spmv(s, s->vy.p, s->vv.p, false, 0.0, 0, nullptr, nullptr, EPI_NONE, 0));
+            bytes = nnzb * blk + 4 * (N + 1) + 16 * b * N;
+            break;
+        case 1:
+            TRY(prec_apply(s, s->vr.p, s->vy.p, 1, 0));
+            bytes = s->prec == PREC_ILU0 ? nnzb * blk + 32 * b * N + 16 * (N + 1) + 8 * N
+                                         : (nnzb - N) * blk + 16 * b * b * N + 40 * b * N + 16 * (N + 1) + 8 * N;
+            break;
+        case 2:
+            TRY(relayout(s, s->vals_native.p));
+            TRY(prec_update(s));
+            bytes = 2 * nnzb * blk + 16 * b * b * N;
+            break;
+        case 3:
+            vec_p_update_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);
+            vec_half1_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);
+            vec_half2_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);
+            s->launches += 2;
+            TRY(check_launch(s, "vector kernels"));
+            bytes = 17 * 8 * b * N;
+            break;
+        default:
+            return fail(OPMB200_INVALID_ARGUMENT, "unknown kernel id");
+        }
+    }
+    CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+    *ms_per_launch = ms / reps;
+    if (algorithmic_bytes)
+        *algorithmic_bytes = bytes;
+    return OPMB200_SUCCESS;
+}
+
+} // extern "C"

@@ -47,7 +47,7 @@ def mobility_template(b: int):
 
 
 def blackoil_system(nx, ny, nz, b=3, seed=1000, sigma=2.0, kz_mult=1.0, z_range=None,
-                    n_active=None, nnc=0, acc=(0.02, 1.0, 1.0, 1.0), pert=0.05, with_rhs=True):
+                    n_active=None, nnc=0, acc=(0.005, 1.0, 1.0, 1.0), pert=0.05, with_rhs=True):
     """Build rows of the cells in planes z_range=[z0,z1) (default: all) of an nx x ny x nz grid.
 
     Returns dict(A=BCSR with GLOBAL column indices restricted... see below, ...):
@@ -99,7 +99,7 @@ def blackoil_system(nx, ny, nz, b=3, seed=1000, sigma=2.0, kz_mult=1.0, z_range=
             Mo = M_dn if upstream else M_up   # block multiplying the NEIGHBOUR's unknowns
             Md = M_up if upstream else M_dn   # this cell's own contribution to its diagonal
             offblk = -Tf[..., None, None] * (Mo + pert * R[d])
-            diag[k - z0] += Tf[..., None, None] * (Md + pert * R[d][..., ::-1, ::-1])
+            diag[k - z0] += Tf[..., None, None] * (Md + pert * R[d])
             tsum[k - z0] += Tf
             sel = ok
             rows_l.append(cell[sel])

@@ -1,0 +1,302 @@
+"""GPU parity tests: everything goes through the C ABI (libopmb200.so, CUDA kernels) and is checked
+against the CPU oracle on the same inputs.  Bars (BASELINE.json north_star): level sets and reorder
+maps bit-exact; SpMV / preconditioner apply / solution within 1e-10 relative (fp64); BiCGSTAB
+iteration counts identical or +-1; the reference's golden solutions within its own 1e-3 percent."""
+import numpy as np
+import pytest
+
+from conftest import coo_to_bcsr, pattern_to_bcsr, rel_err
+from opm_simulators_b200 import _lib, generators
+from opm_simulators_b200.flexible_solver import (FlexibleSolver, ISTLSolverB200, MatrixAdapter, MatrixBlockError,
+                                                 NumericalProblem, SolverAbort)
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def opts(prec, tol=1e-2, maxiter=200, relaxation=None, **extra):
+    p = {"type": prec}
+    if relaxation is not None:
+        p["relaxation"] = relaxation
+    d = {"solver": "bicgstab", "tol": tol, "maxiter": maxiter, "verbosity": 0, "preconditioner": p}
+    d.update(extra)
+    return d
+
+
+def systems():
+    rng = np.random.default_rng(42)
+    yield "lap3d_b1", generators.laplace_like(7, 1, rng, dims=3, asym=0.2)
+    yield "lap3d_b2", generators.laplace_like(6, 2, rng, dims=3, asym=0.2)
+    yield "lap2d_b3", generators.laplace_like(23, 3, rng, dims=2, asym=0.3)
+    yield "lap3d_b4", generators.laplace_like(6, 4, rng, dims=3, asym=0.1)
+    yield "blackoil_b3", generators.blackoil_system(9, 8, 7, b=3, seed=11)["A"]
+    yield "blackoil_b4", generators.blackoil_system(6, 7, 5, b=4, seed=12)["A"]
+    yield "c2like_b3", generators.config("C2", scale=0.3, with_rhs=False)["A"]
+    yield "asym_b3", pattern_to_bcsr([[0, 2], [0, 1], [1, 2, 3], [0, 3]], 3, rng)
+    yield "single_row", pattern_to_bcsr([[0]], 3, rng)
+
+
+SYSTEMS = dict(systems())
+
+
+# ---- the reference's golden vectors through the CUDA path ---------------------------------------
+@pytest.mark.parametrize("b", [1, 3])
+@pytest.mark.parametrize("prec", ["ilu0", "dilu"])
+def test_matr33_golden_solution(golden, b, prec):
+    """tests/test_flexiblesolver.cpp:83-130 with tests/options_flexiblesolver_1x1.json"""
+    A = coo_to_bcsr(golden["matr33"], b)
+    o = dict(golden["options_flexiblesolver_1x1"])
+    o["preconditioner"] = {"type": prec}
+    o["verbosity"] = "0"
+    fs = FlexibleSolver(MatrixAdapter(A), o)
+    x, rhs = np.zeros(9), np.array(golden["rhs3"])
+    res = fs.apply(x, rhs)
+    xo, ro, _ = orc.solve_serial(A.rowptr, A.col, A.val, golden["rhs3"], prec=prec, tol=0.5, maxiter=20)
+    assert res.converged and res.iterations == ro["iterations"]
+    assert rel_err(x, xo) < 1e-9
+    if b == 3 or prec == "ilu0":
+        assert np.allclose(x, golden["matr33_solution"], rtol=golden["matr33_solution_tol_percent"] / 100)
+
+
+@pytest.mark.parametrize("b", [1, 3])
+def test_matr33rep_unpreconditioned_golden(golden, b):
+    """tests/test_preconditionerfactory.cpp:231-376: plain BiCGSTAB on the RepeatingOperator A*A"""
+    A = coo_to_bcsr(golden["matr33rep"], b)
+    o = dict(golden["options_flexiblesolver_simple"])
+    o["b200"] = {"operator_repeats": golden["matr33rep_repeats"]}
+    from opm_simulators_b200.flexible_solver import PreconditionerFactory, PreconditionerWithUpdate
+    PreconditionerFactory.addCreator("nothing", lambda op, prm: PreconditionerWithUpdate(op, prm))
+    fs = FlexibleSolver(MatrixAdapter(A), o)
+    x, rhs = np.zeros(9), np.array(golden["rhs3rep"], float)
+    res = fs.apply(x, rhs)
+    xo, ro, ho = orc.solve_serial(A.rowptr, A.col, A.val, golden["rhs3rep"], prec="nothing", tol=1e-12, maxiter=200,
+                                  op_repeats=2)
+    assert res.converged
+    assert np.allclose(x, golden["matr33rep_solution"], rtol=golden["matr33rep_solution_tol_percent"] / 100)
+    assert abs(res.iterations - ro["iterations"]) <= 1
+
+
+def test_solver_adapter_tridiagonal():
+    """tests/gpuistl/test_solver_adapter.cpp:88-117"""
+    n, b = 10, 3
+    A = pattern_to_bcsr([[j for j in (i - 1, i, i + 1) if 0 <= j < n] for i in range(n)], b)
+    r = A.row_of_entry()
+    A.val[:] = np.where((r == A.col)[:, None, None], -2.0, 1.0) * np.eye(b)
+    fs = FlexibleSolver(MatrixAdapter(A), opts("ilu0", tol=1e-12))
+    rhs = np.zeros(n * b)
+    fs.op.apply(np.ones(n * b), rhs)
+    x = np.repeat(0.1 * np.arange(n), b)
+    res = fs.apply(x, rhs)
+    assert res.converged and np.allclose(x, 1.0, rtol=1e-11)
+
+
+# ---- integer artefacts: bit-exact ---------------------------------------------------------------
+@pytest.mark.parametrize("name", list(SYSTEMS))
+def test_levels_and_reorder_bit_exact(name):
+    A = SYSTEMS[name]
+    fs = FlexibleSolver(MatrixAdapter(A), opts("dilu"))
+    ptr, rows = fs.levels()
+    _, rows_o, ptr_o = orc.row_coloring(A.rowptr, A.col, orc.COLOR_LOWER)
+    assert np.array_equal(ptr, ptr_o) and np.array_equal(rows, rows_o)
+    r2n, n2r = fs.reorder()
+    r2n_o, n2r_o = orc.reorder_maps(rows_o)
+    assert np.array_equal(r2n, r2n_o) and np.array_equal(n2r, n2r_o)
+    assert fs.info()["n_levels"] == len(ptr_o) - 1
+
+
+# ---- SpMV ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(SYSTEMS))
+def test_spmv_parity(name):
+    A = SYSTEMS[name]
+    rng = np.random.default_rng(1)
+    fs = FlexibleSolver(MatrixAdapter(A), opts("dilu"))
+    x = rng.standard_normal(A.n * A.b)
+    y = np.full(A.n * A.b, np.nan)
+    fs.op.apply(x, y)
+    assert rel_err(y, orc.spmv(A.rowptr, A.col, A.val, x)) < TOL
+    y0 = rng.standard_normal(A.n * A.b)
+    y1 = y0.copy()
+    fs.op.applyscaleadd(-1.0, x, y1)
+    assert rel_err(y1, orc.spmv_scaleadd(A.rowptr, A.col, A.val, -1.0, x, y0)) < TOL
+    assert abs(fs.dot(x, y0) - float(x @ y0)) <= 1e-12 * np.linalg.norm(x) * np.linalg.norm(y0)
+
+
+# ---- DILU ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(SYSTEMS))
+def test_dilu_parity(name):
+    A = SYSTEMS[name]
+    rng = np.random.default_rng(2)
+    fs = FlexibleSolver(MatrixAdapter(A), opts("dilu"))
+    dinv_o = orc.dilu_update(A.rowptr, A.col, A.val)
+    assert rel_err(fs.dinv(), dinv_o) < TOL
+    for _ in range(2):  # twice: the sweeps re-arm their own synchronisation state
+        d = rng.standard_normal(A.n * A.b)
+        v = np.zeros_like(d)
+        fs.preconditioner().apply(v, d)
+        assert rel_err(v, orc.dilu_apply(A.rowptr, A.col, A.val, dinv_o, d)) < TOL
+
+
+# ---- ILU0 -----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(SYSTEMS))
+@pytest.mark.parametrize("w", [1.0, 0.9])
+def test_ilu0_parity(name, w):
+    A = SYSTEMS[name]
+    rng = np.random.default_rng(3)
+    fs = FlexibleSolver(MatrixAdapter(A), opts("ilu0", relaxation=w))
+    lu_o = orc.ilu0_decompose(A.rowptr, A.col, A.val)
+    assert rel_err(fs.ilu0(), lu_o) < TOL
+    for _ in range(2):
+        d = rng.standard_normal(A.n * A.b)
+        v = np.zeros_like(d)
+        fs.preconditioner().apply(v, d)
+        assert rel_err(v, orc.ilu0_apply(A.rowptr, A.col, lu_o, d, relaxation=w)) < TOL
+
+
+# ---- whole solves ----------------------------------------------------------------------------------------
+SOLVE_CASES = [
+    ("C2", 0.4, "dilu", 1e-2, {}), ("C2", 0.4, "ilu0", 1e-2, {"relaxation": 0.9}),
+    ("C3", 0.25, "dilu", 1e-2, {}), ("C3", 0.25, "ilu0", 1e-2, {}),
+    ("C3", 0.2, "dilu", 1e-8, {}), ("C3", 0.2, "ilu0", 1e-8, {"relaxation": 0.9}),
+    ("C5", 0.12, "dilu", 1e-4, {}), ("C5", 0.12, "ilu0", 1e-4, {}),
+]
+
+
+@pytest.mark.parametrize("cfg,scale,prec,tol,pk", SOLVE_CASES)
+def test_bicgstab_solve_parity(cfg, scale, prec, tol, pk):
+    s = generators.config(cfg, scale=scale)
+    A = s["A"]
+    for rhs_name in ("rhs", "rhs2"):
+        fs = FlexibleSolver(MatrixAdapter(A), opts(prec, tol=tol, **pk))
+        x, r = np.zeros(A.n * A.b), s[rhs_name].copy()
+        res = fs.apply(x, r)
+        xo, ro, ho = orc.solve_serial(A.rowptr, A.col, A.val, s[rhs_name], prec=prec, tol=tol, maxiter=200,
+                                      relaxation=pk.get("relaxation", 1.0))
+        h = fs.history()
+        assert res.converged == bool(ro["converged"])
+        assert abs(res.iterations - ro["iterations"]) <= 1, (res.iterations, ro["iterations"])
+        if len(h) == len(ho):  # same stopping half-step: solutions agree to rounding
+            assert rel_err(x, xo) < 1e-8, rel_err(x, xo)
+            assert np.allclose(h, ho, rtol=1e-6)
+            # the residual vector Dune leaves in b
+            res_true = s[rhs_name] - orc.spmv(A.rowptr, A.col, A.val, x)
+            assert rel_err(r, res_true) < 1e-6
+        assert abs(res.reduction - h[-1] / h[0]) < 1e-14
+        true_red = np.linalg.norm(s[rhs_name] - orc.spmv(A.rowptr, A.col, A.val, x)) / np.linalg.norm(s[rhs_name])
+        assert true_red < tol * 1.01
+        fs.close()
+
+
+def test_tight_tolerance_recovers_xstar():
+    s = generators.config("C3", scale=0.2)
+    A = s["A"]
+    fs = FlexibleSolver(MatrixAdapter(A), opts("dilu", tol=1e-12, maxiter=400))
+    x, r = np.zeros(A.n * 3), s["rhs"].copy()
+    res = fs.apply(x, r)
+    assert res.converged and rel_err(x, s["xstar"]) < 1e-8
+
+
+def test_prepare_solve_cycle_with_value_refresh():
+    """AbstractISTLSolver usage of Flow: prepare(M,b); solve(x); new values, same pattern; again.
+    (NonlinearSystemBlackOilReservoir_impl.hpp:459-469, ISTLSolver.hpp:499-530)"""
+    s = generators.config("C2", scale=0.35)
+    A = s["A"]
+    solver = ISTLSolverB200(opts("dilu", tol=1e-6))
+    rng = np.random.default_rng(5)
+    for step in range(3):
+        M = A.copy()
+        M.val *= (1.0 + 0.1 * step)
+        M.val[M.diag_index()] += 0.05 * step * np.eye(3)
+        b = rng.standard_normal(A.n * 3)
+        x = np.zeros(A.n * 3)
+        solver.prepare(M, b.copy())
+        assert solver.solve(x)
+        xo, ro, _ = orc.solve_serial(M.rowptr, M.col, M.val, b, prec="dilu", tol=1e-6)
+        assert abs(solver.iterations() - ro["iterations"]) <= 1
+        assert rel_err(x, xo) < 1e-5
+    assert solver.getSolveCount() == 3
+
+
+def test_maxiter_and_convergence_verdict():
+    s = generators.config("C3", scale=0.2)
+    A = s["A"]
+    solver = ISTLSolverB200(opts("dilu", tol=1e-14, maxiter=3), relaxed_linear_solver_reduction=1e-30)
+    solver.prepare(A, s["rhs"].copy())
+    x = np.zeros(A.n * 3)
+    with pytest.raises(NumericalProblem):
+        solver.solve(x)
+    assert solver.result.iterations == 3 and not solver.result.converged
+    xo, ro, _ = orc.solve_serial(A.rowptr, A.col, A.val, s["rhs"], prec="dilu", tol=1e-14, maxiter=3)
+    assert ro["iterations"] == 3 and rel_err(x, xo) < 1e-9
+    relaxed = ISTLSolverB200(opts("dilu", tol=1e-14, maxiter=3), relaxed_linear_solver_reduction=0.5)
+    relaxed.prepare(A, s["rhs"].copy())
+    assert relaxed.solve(np.zeros(A.n * 3))  # accepted with the reference's "tolerance not achieved" rule
+
+
+def test_zero_rhs_converges_immediately():
+    A = SYSTEMS["blackoil_b3"]
+    fs = FlexibleSolver(MatrixAdapter(A), opts("dilu"))
+    x, r = np.zeros(A.n * 3), np.zeros(A.n * 3)
+    res = fs.apply(x, r)
+    assert res.converged and res.iterations == 0 and not x.any()
+
+
+def test_nan_rhs_is_solver_abort():
+    A = SYSTEMS["blackoil_b3"]
+    fs = FlexibleSolver(MatrixAdapter(A), opts("dilu"))
+    r = np.ones(A.n * 3)
+    r[5] = np.nan
+    with pytest.raises(SolverAbort):
+        fs.apply(np.zeros(A.n * 3), r)
+
+
+def test_singular_4x4_block_is_matrix_block_error():
+    """matrixblock.hh:205-224 -> Dune::MatrixBlockError -> time-step chop in Flow"""
+    A = SYSTEMS["blackoil_b4"].copy()
+    A.val[A.diag_index()[3]] = 0.0
+    with pytest.raises(MatrixBlockError):
+        FlexibleSolver(MatrixAdapter(A), opts("ilu0"))
+    B = SYSTEMS["blackoil_b4"].copy()
+    B.val[B.diag_index()[0]] = 0.0
+    with pytest.raises(MatrixBlockError):
+        FlexibleSolver(MatrixAdapter(B), opts("dilu"))
+
+
+def test_device_pointers_are_accepted():
+    torch = pytest.importorskip("torch")
+    s = generators.config("C2", scale=0.3)
+    A = s["A"]
+    fs = FlexibleSolver(MatrixAdapter(A), opts("dilu", tol=1e-8))
+    vals = torch.from_numpy(A.val).cuda()
+    fs.update(vals)
+    x = torch.zeros(A.n * 3, dtype=torch.float64, device="cuda")
+    r = torch.from_numpy(s["rhs"]).cuda()
+    res = fs.apply(x, r)
+    torch.cuda.synchronize()
+    xo, ro, _ = orc.solve_serial(A.rowptr, A.col, A.val, s["rhs"], prec="dilu", tol=1e-8)
+    assert abs(res.iterations - ro["iterations"]) <= 1 and rel_err(x.cpu().numpy(), xo) < 1e-6
+
+
+def test_wide_rows_beyond_the_register_window():
+    """rows with more than 3 lower / upper blocks (NNC- or well-like) take the streaming path"""
+    rng = np.random.default_rng(8)
+    n = 200
+    dense = np.eye(n, dtype=bool)
+    for i in range(n):
+        for j in rng.choice(n, 6, replace=False):
+            dense[i, j] = dense[j, i] = True
+    from opm_simulators_b200.bcsr import BCSR
+    A = BCSR.from_dense_pattern(dense, 3, rng=rng)
+    A.val[A.diag_index()] += 12 * np.eye(3)
+    for prec in ("dilu", "ilu0"):
+        fs = FlexibleSolver(MatrixAdapter(A), opts(prec, tol=1e-9))
+        d = rng.standard_normal(n * 3)
+        v = np.zeros(n * 3)
+        fs.preconditioner().apply(v, d)
+        ps = orc.ParSystem.serial(A.rowptr, A.col, A.val)
+        ps.prec_update(prec)
+        assert rel_err(v, ps.prec_apply([d])[0]) < TOL
+        x, r = np.zeros(n * 3), d.copy()
+        res = fs.apply(x, r)
+        xo, ro, _ = orc.solve_serial(A.rowptr, A.col, A.val, d, prec=prec, tol=1e-9)
+        assert abs(res.iterations - ro["iterations"]) <= 1 and rel_err(x, xo) < 1e-6
