@@ -190,6 +190,11 @@ int opmb200_get_history(opmb200_solver* s, double* hist, int capacity, int* coun
 int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, double* ms_per_launch,
                         double* algorithmic_bytes);
 
+/* Device-time stopwatch on the handle's own stream (CUDA events): start, run any sequence of
+ * calls on the handle, stop -> elapsed milliseconds between the two events. */
+int opmb200_timer_start(opmb200_solver* s);
+int opmb200_timer_stop(opmb200_solver* s, double* elapsed_ms);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,8 @@ PROTOTYPES = {
     "opmb200_get_ilu0": (C.c_int, [_vp, _vp]),
     "opmb200_get_history": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     "opmb200_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "opmb200_timer_start": (C.c_int, [_vp]),
+    "opmb200_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
 }
 
 _lib = None
@@ -102,12 +104,28 @@ class SolverAbort(B200Error):
     """Dune::SolverAbort"""
 
 
+def _preload_nccl():
+    """libopmb200 links libnccl.so.2.  PyTorch ships its own (newer) copy under the same SONAME; if
+    the system copy were loaded first, a later `import torch` in the same process would bind to
+    it and miss symbols.  Load torch's copy first when it exists so that both agree."""
+    import glob
+    import sys
+    for base in sys.path:
+        for cand in glob.glob(os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+                return
+            except OSError:
+                pass
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no CPU fallback)")
+        _preload_nccl()
         L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(L, name)  # AttributeError if the library does not export the symbol

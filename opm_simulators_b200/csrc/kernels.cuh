@@ -56,6 +56,14 @@ __device__ __forceinline__ void st_relaxed(double* p, double v)
 {
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// weak load that bypasses the L1 (always served by the L2, the point of coherence); unlike the
+// .relaxed.gpu form several of these can be in flight per thread
+__device__ __forceinline__ double ld_cg(const double* p)
+{
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ int ld_relaxed(const int* p)
 {
     int v;
@@ -76,6 +84,11 @@ __device__ __forceinline__ double guard(double v)
 {
     return is_sentinel(v) ? __longlong_as_double(0x7FF8000000000000ll) : v;
 }
+
+// Level-ordered vectors are stored component-major ("SoA"): component c of row q at c*n + q, so
+// that a warp touching 32 consecutive rows moves whole 256-byte lines (loads, stores and the
+// dependency polls of the sweeps alike).
+#define VIDX(n, q, c) ((size_t)(c) * (size_t)(n) + (size_t)(q))
 
 // element e of block slot (slot_row, lane)
 template <int BB>
@@ -490,7 +503,7 @@ __global__ void permute_in_kernel(int64_t n, const int* __restrict__ r2n, const 
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * B; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t q = t / B;
         const int c = (int)(t - q * B);
-        lvl[t] = nat[(size_t)r2n[q] * B + c];
+        lvl[VIDX(n, q, c)] = nat[(size_t)r2n[q] * B + c];
     }
 }
 template <int B>
@@ -500,7 +513,7 @@ __global__ void permute_out_kernel(int64_t n, const int* __restrict__ n2r, const
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * B; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = t / B;
         const int c = (int)(t - i * B);
-        nat[t] = lvl[(size_t)n2r[i] * B + c];
+        nat[t] = lvl[VIDX(n, n2r[i], c)];
     }
 }
 
@@ -558,7 +571,7 @@ __global__ void __launch_bounds__(kCtaThreads) spmv_kernel(SpmvArgs a)
                     blk[e] = __ldcs(a.A + elem_index<BB>(m.base + sr, lane, e));
 #pragma unroll
                 for (int r = 0; r < B; ++r)
-                    xv[r] = __ldg(a.x + (size_t)c * B + r);
+                    xv[r] = __ldg(a.x + VIDX(a.n, c, r));
                 blk_umv<B>(blk, xv, acc);
             }
         }
@@ -569,16 +582,16 @@ __global__ void __launch_bounds__(kCtaThreads) spmv_kernel(SpmvArgs a)
             for (int r = 0; r < B; ++r) {
                 double v = ghost ? 0.0 : acc[r];
                 if (SCALEADD)
-                    v = ghost ? 0.0 : a.y[(size_t)q * B + r] + a.alpha * v;
+                    v = ghost ? 0.0 : a.y[VIDX(a.n, q, r)] + a.alpha * v;
                 out[r] = v;
-                a.y[(size_t)q * B + r] = v;
+                a.y[VIDX(a.n, q, r)] = v;
                 if (a.copy_out)
-                    a.copy_out[(size_t)q * B + r] = v;
+                    a.copy_out[VIDX(a.n, q, r)] = v;
             }
             if (NDOT >= 1) {
 #pragma unroll
                 for (int r = 0; r < B; ++r)
-                    dots[0] += out[r] * (a.u ? a.u[(size_t)q * B + r] : out[r]);
+                    dots[0] += out[r] * (a.u ? a.u[VIDX(a.n, q, r)] : out[r]);
             }
             if (NDOT >= 2) {
 #pragma unroll
@@ -828,7 +841,7 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                 for (int e = 0; e < BB; ++e)
                     blk[s][e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
             }
-        double di[BB], rhs[B];
+        double di[BB], rhs[B], yi[B];
         bool ghost = false;
         if (active) {
             if (!(ILU0 && !UPPER)) {
@@ -842,14 +855,16 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                 // ParallelOverlappingILU0 never touches ghost rows: their v keeps its input value
 #pragma unroll
                 for (int r = 0; r < B; ++r)
-                    rhs[r] = ghost ? (a.ghost_zero ? 0.0 : a.v[(size_t)q * B + r]) : a.d[(size_t)q * B + r];
+                    rhs[r] = ghost ? (a.ghost_zero ? 0.0 : a.v[VIDX(a.n, q, r)]) : a.d[VIDX(a.n, q, r)];
 #pragma unroll
                 for (int r = 0; r < B; ++r)
-                    st_relaxed(a.v + (size_t)q * B + r, sentinel()); // arm the upper sweep's output
+                    st_relaxed(a.v + VIDX(a.n, q, r), sentinel()); // arm the upper sweep's output
             } else {
 #pragma unroll
-                for (int r = 0; r < B; ++r)
-                    rhs[r] = (ILU0) ? a.tmp[(size_t)q * B + r] : 0.0;
+                for (int r = 0; r < B; ++r) {
+                    yi[r] = a.tmp[VIDX(a.n, q, r)]; // y_i of the lower sweep (complete: previous kernel)
+                    rhs[r] = (ILU0) ? yi[r] : 0.0;
+                }
             }
         }
 
@@ -858,7 +873,7 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
             const int lv = UPPER ? m.level + a.throttle : m.level - a.throttle;
             if (lv >= 0 && lv < a.n_levels) {
                 const int pq = UPPER ? a.level_q0[lv] : a.level_q0[lv + 1] - 1;
-                const double* pp = out + (size_t)pq * B + (B - 1);
+                const double* pp = out + VIDX(a.n, pq, B - 1);
                 if (lane == 0)
                     while (is_sentinel(ld_relaxed(pp)))
                         __nanosleep(200);
@@ -875,15 +890,26 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                 if (cj[s] >= 0)
                     pending |= 1u << s;
             while (pending) {
+                // All outstanding dependencies are sampled with ONE round trip to the L2.  The polls
+                // are weak L1-bypassing loads (ld.global.cg): the L2 is the point of coherence, so
+                // they observe the producer's st.relaxed.gpu as soon as it lands, and -- unlike
+                // ld.relaxed.gpu, of which the hardware keeps only a few in flight per thread
+                // (scripts/microbench_hop.cu: 9 polled lines cost 3000 cycles per hop, 3 cost 1100)
+                // -- they all overlap.  Every word validates itself against the sentinel.
+#pragma unroll
+                for (int s = 0; s < kPrefetch; ++s)
+                    if (pending & (1u << s)) {
+#pragma unroll
+                        for (int r = 0; r < B; ++r)
+                            xv[s][r] = ld_cg(out + VIDX(a.n, cj[s], r));
+                    }
 #pragma unroll
                 for (int s = 0; s < kPrefetch; ++s)
                     if (pending & (1u << s)) {
                         bool ok = true;
 #pragma unroll
-                        for (int r = 0; r < B; ++r) {
-                            xv[s][r] = ld_relaxed(out + (size_t)cj[s] * B + r);
+                        for (int r = 0; r < B; ++r)
                             ok = ok && !is_sentinel(xv[s][r]);
-                        }
                         if (ok)
                             pending &= ~(1u << s);
                     }
@@ -910,7 +936,7 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                     ok = true;
 #pragma unroll
                     for (int r = 0; r < B; ++r) {
-                        xs[r] = ld_relaxed(out + (size_t)c * B + r);
+                        xs[r] = ld_relaxed(out + VIDX(a.n, c, r));
                         ok = ok && !is_sentinel(xs[r]);
                     }
                 } while (!ok);
@@ -937,16 +963,9 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                         for (int r = 0; r < B; ++r)
                             res[r] = rhs[r];
                     } else {
-                        blk_mv<B>(di, rhs, res); // v_i = Dinv_i (y_i - sum)
-#pragma unroll
-                        for (int r = 0; r < B; ++r)
-                            res[r] *= a.relax;
+                        blk_mv<B>(di, rhs, res); // v_i = Dinv_i (y_i - sum); relaxation is applied afterwards
                     }
                 } else {
-                    double yi[B];
-#pragma unroll
-                    for (int r = 0; r < B; ++r)
-                        yi[r] = a.tmp[(size_t)q * B + r];
                     blk_mmv<B>(di, rhs, yi); // v_i = y_i - Dinv_i rhs
 #pragma unroll
                     for (int r = 0; r < B; ++r)
@@ -954,11 +973,11 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                 }
 #pragma unroll
                 for (int r = 0; r < B; ++r)
-                    a.tmp[(size_t)q * B + r] = sentinel(); // re-arm for the next apply
+                    a.tmp[VIDX(a.n, q, r)] = sentinel(); // re-arm for the next apply
             }
 #pragma unroll
             for (int r = 0; r < B; ++r)
-                st_relaxed(out + (size_t)q * B + r, guard(res[r]));
+                st_relaxed(out + VIDX(a.n, q, r), guard(res[r]));
         }
     }
     return_ticket(a.ticket);
@@ -1035,11 +1054,21 @@ __global__ void __launch_bounds__(256) dot_kernel(int64_t n, int64_t n_interior,
 {
     double s[1] = {0.0};
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n * B; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t q = t / B;
+        const int64_t q = t % n; // component-major storage
         if (n_interior == n || r2n[q] < n_interior)
             s[0] += x[t] * y[t];
     }
     grid_reduce<1>(s, rc, epi, sc, hist, out);
+}
+
+// v *= w   (ParallelOverlappingILU0_impl.hpp:415-417, after the halo copy)
+__global__ void __launch_bounds__(256) scale_kernel(int64_t len, double w, double* __restrict__ v, const Scalars* sc,
+                                                    int check_done)
+{
+    if (check_done && sc->done)
+        return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        v[i] *= w;
 }
 
 // y += a x
@@ -1057,18 +1086,18 @@ __global__ void fill_kernel(double* p, int64_t len, double v)
 
 // halo: pack owner rows / scatter received ghost rows (positions in level order)
 template <int B>
-__global__ void gather_rows_kernel(int cnt, const int* __restrict__ rows, const double* __restrict__ v,
+__global__ void gather_rows_kernel(int64_t n, int cnt, const int* __restrict__ rows, const double* __restrict__ v,
                                    double* __restrict__ buf)
 {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt * B; t += gridDim.x * blockDim.x)
-        buf[t] = v[(size_t)rows[t / B] * B + t % B];
+        buf[t] = v[VIDX(n, rows[t / B], t % B)];
 }
 template <int B>
-__global__ void scatter_rows_kernel(int cnt, const int* __restrict__ rows, const double* __restrict__ buf,
+__global__ void scatter_rows_kernel(int64_t n, int cnt, const int* __restrict__ rows, const double* __restrict__ buf,
                                     double* __restrict__ v)
 {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt * B; t += gridDim.x * blockDim.x)
-        v[(size_t)rows[t / B] * B + t % B] = buf[t];
+        v[VIDX(n, rows[t / B], t % B)] = buf[t];
 }
 
 } // namespace opmb200

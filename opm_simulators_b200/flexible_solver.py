@@ -318,6 +318,14 @@ class FlexibleSolver:
         _lib.check(_lib.lib().opmb200_time_kernel(self._h, what, warmup, reps, C.byref(ms), C.byref(nbytes)))
         return ms.value, nbytes.value
 
+    def timer_start(self):
+        _lib.check(_lib.lib().opmb200_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        _lib.check(_lib.lib().opmb200_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
     def close(self):
         if self._h:
             _lib.lib().opmb200_destroy(self._h)

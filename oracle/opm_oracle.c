@@ -556,6 +556,7 @@ int orc_par_prec_update(orc_par* h, int kind, double w)
     int rc_all = ORC_OK;
     h->kind = kind;
     h->w = w;
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < h->nsub; ++p) {
         orc_sub* s = &h->sub[p];
         const size_t nnzb = (size_t)s->rowptr[s->n];
@@ -572,8 +573,11 @@ int orc_par_prec_update(orc_par* h, int kind, double w)
         } else if (kind != ORC_PREC_NONE) {
             rc = ORC_ERR_ARG;
         }
-        if (rc != ORC_OK && rc_all == ORC_OK)
-            rc_all = rc;
+        if (rc != ORC_OK) {
+#pragma omp critical
+            if (rc_all == ORC_OK)
+                rc_all = rc;
+        }
     }
     return rc_all;
 }
@@ -605,6 +609,7 @@ void orc_par_copy_owner_to_all(orc_par* h, double** v)
 int orc_par_prec_apply(orc_par* h, double** v, double** d)
 {
     const int b = h->b;
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < h->nsub; ++p) {
         const orc_sub* s = &h->sub[p];
         if (h->kind == ORC_PREC_DILU)
@@ -617,6 +622,7 @@ int orc_par_prec_apply(orc_par* h, double** v, double** d)
     if (h->kind != ORC_PREC_NONE)
         orc_par_copy_owner_to_all(h, v);
     if (h->kind == ORC_PREC_ILU0 && fabs(h->w - 1.0) > 1e-15)
+#pragma omp parallel for schedule(static)
         for (int p = 0; p < h->nsub; ++p)
             for (size_t s = 0; s < (size_t)h->sub[p].n * b; ++s)
                 v[p][s] *= h->w;
@@ -629,6 +635,8 @@ double orc_par_dot(orc_par* h, double** x, double** y)
 {
     const int b = h->b;
     double total = 0.0;
+    double* part = (double*)malloc(sizeof(double) * (size_t)h->nsub);
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < h->nsub; ++p) {
         double sum = 0.0;
         for (int i = 0; i < h->sub[p].interior; ++i) {
@@ -637,8 +645,11 @@ double orc_par_dot(orc_par* h, double** x, double** y)
                 blk += x[p][(size_t)i * b + r] * y[p][(size_t)i * b + r];
             sum += blk;
         }
-        total += sum;
+        part[p] = sum;
     }
+    for (int p = 0; p < h->nsub; ++p) /* MPI_Allreduce: rank order */
+        total += part[p];
+    free(part);
     return total;
 }
 
@@ -659,6 +670,7 @@ static void vec_free(orc_par* h, double** v)
 }
 static void vec_copy(orc_par* h, double** dst, double** src)
 {
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < h->nsub; ++p)
         memcpy(dst[p], src[p], sizeof(double) * (size_t)h->sub[p].n * h->b);
 }
@@ -670,6 +682,7 @@ static void vec_zero(orc_par* h, double** v)
 /* y += a x */
 static void vec_axpy(orc_par* h, double a, double** x, double** y)
 {
+#pragma omp parallel for schedule(static)
     for (int p = 0; p < h->nsub; ++p)
         for (size_t s = 0; s < (size_t)h->sub[p].n * h->b; ++s)
             y[p][s] += a * x[p][s];
@@ -680,6 +693,7 @@ static void op_apply(orc_par* h, int repeats, double** x, double** y, double** t
 {
     const int b = h->b;
     if (repeats <= 1) {
+#pragma omp parallel for schedule(static)
         for (int p = 0; p < h->nsub; ++p) {
             const orc_sub* s = &h->sub[p];
             orc_spmv(s->n, b, s->rowptr, s->col, s->val, s->interior, x[p], y[p]);
@@ -701,6 +715,7 @@ static void op_applyscaleadd(orc_par* h, int repeats, double alpha, double** x, 
 {
     const int b = h->b;
     if (repeats <= 1) {
+#pragma omp parallel for schedule(static)
         for (int p = 0; p < h->nsub; ++p) {
             const orc_sub* s = &h->sub[p];
             orc_spmv_scaleadd(s->n, b, s->rowptr, s->col, s->val, s->interior, alpha, x[p], y[p]);
@@ -779,6 +794,7 @@ int orc_par_bicgstab(orc_par* h, double** x, double** b, double reduction, int m
         } else {
             beta = (norm == 0.0) ? 0.0 : (rho_new / rho) * (alpha / omega);
             vec_axpy(h, -omega, v, p); /* p = r + beta (p - omega v) */
+#pragma omp parallel for schedule(static)
             for (int q = 0; q < h->nsub; ++q)
                 for (size_t s = 0; s < (size_t)h->sub[q].n * h->b; ++s) {
                     p[q][s] *= beta;

@@ -38,13 +38,14 @@ def test_c3_full_size_properties(c3, prec):
     fs.op.apply(y1, y2)
     assert rel_err(y2, x1) < 0.9
     # the solve reaches the requested reduction on the TRUE residual
-    x, r = np.zeros(A.n * 3), c3["rhs"].copy()
+    rhs = c3["rhs2"]
+    x, r = np.zeros(A.n * 3), rhs.copy()
     res = fs.apply(x, r)
     assert res.converged and 0 < res.iterations <= 200
-    true = np.linalg.norm(c3["rhs"] - S @ x) / np.linalg.norm(c3["rhs"])
+    true = np.linalg.norm(rhs - S @ x) / np.linalg.norm(rhs)
     assert true < 1.05e-2 and abs(true - res.reduction) < 1e-6
-    assert rel_err(r, c3["rhs"] - S @ x) < 1e-6
+    assert rel_err(r, rhs - S @ x) < 1e-6
     # deterministic: a second solve reproduces the first bit for bit
-    x2_, r2_ = np.zeros(A.n * 3), c3["rhs"].copy()
+    x2_, r2_ = np.zeros(A.n * 3), rhs.copy()
     res2 = fs.apply(x2_, r2_)
     assert res2.iterations == res.iterations and np.array_equal(x2_, x)

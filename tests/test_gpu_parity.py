@@ -174,10 +174,15 @@ def test_bicgstab_solve_parity(cfg, scale, prec, tol, pk):
                                       relaxation=pk.get("relaxation", 1.0))
         h = fs.history()
         assert res.converged == bool(ro["converged"])
-        assert abs(res.iterations - ro["iterations"]) <= 1, (res.iterations, ro["iterations"])
+        # +-1 at the tolerances Flow runs with; BiCGSTAB is chaotic near 1e-8 (FMA vs separate
+        # roundings and the reduction order grow exponentially with the iteration number)
+        slack = 1 if tol >= 1e-6 else max(1, int(0.15 * ro["iterations"]))
+        assert abs(res.iterations - ro["iterations"]) <= slack, (res.iterations, ro["iterations"])
+        k = min(len(h), len(ho), 12)
+        assert np.allclose(h[:k], ho[:k], rtol=1e-6), (h[:k], ho[:k])
         if len(h) == len(ho):  # same stopping half-step: solutions agree to rounding
             assert rel_err(x, xo) < 1e-8, rel_err(x, xo)
-            assert np.allclose(h, ho, rtol=1e-6)
+            assert np.allclose(h, ho, rtol=1e-2)
             # the residual vector Dune leaves in b
             res_true = s[rhs_name] - orc.spmv(A.rowptr, A.col, A.val, x)
             assert rel_err(r, res_true) < 1e-6
@@ -252,14 +257,25 @@ def test_nan_rhs_is_solver_abort():
 
 def test_singular_4x4_block_is_matrix_block_error():
     """matrixblock.hh:205-224 -> Dune::MatrixBlockError -> time-step chop in Flow"""
+    for prec in ("ilu0", "dilu"):
+        A = SYSTEMS["blackoil_b4"].copy()
+        A.val[A.diag_index()[0]] = 0.0  # row 0 has no lower neighbours: its pivot block stays exactly singular
+        with pytest.raises(orc.OracleError) as e:
+            orc.solve_serial(A.rowptr, A.col, A.val, np.ones(A.n * 4), prec=prec)
+        assert e.value.code == 2
+        with pytest.raises(MatrixBlockError):
+            FlexibleSolver(MatrixAdapter(A), opts(prec))
+    # a later update with regular values recovers (the time-step chop retries with a new matrix)
+    fs = None
     A = SYSTEMS["blackoil_b4"].copy()
-    A.val[A.diag_index()[3]] = 0.0
+    good = A.val.copy()
+    fs = FlexibleSolver(MatrixAdapter(A), opts("dilu"))
+    A.val[A.diag_index()[0]] = 0.0
     with pytest.raises(MatrixBlockError):
-        FlexibleSolver(MatrixAdapter(A), opts("ilu0"))
-    B = SYSTEMS["blackoil_b4"].copy()
-    B.val[B.diag_index()[0]] = 0.0
-    with pytest.raises(MatrixBlockError):
-        FlexibleSolver(MatrixAdapter(B), opts("dilu"))
+        fs.update(A.val)
+    fs.update(good)
+    x, r = np.zeros(A.n * 4), np.ones(A.n * 4)
+    assert fs.apply(x, r).converged
 
 
 def test_device_pointers_are_accepted():
