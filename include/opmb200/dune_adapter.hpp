@@ -1,0 +1,215 @@
+// dune_adapter.hpp -- the thin C++ -> C-ABI layer that makes libopmb200 a drop-in behind the
+// reference's own interfaces.  Header-only; compiles inside an OPM build (needs dune-istl and
+// opm-simulators headers) -- in this repository it is compile- and run-checked against the
+// minimal stand-ins of tests/cpp/stubs (same class and member names).
+//
+//   Opm::b200::Solver<Operator>          : Dune::InverseOperator<X,X>
+//        what FlexibleSolver::initSolver instantiates for   "solver": "b200bicgstab"
+//        (next to "gpubicgstab", FlexibleSolver_impl.hpp:313-321)
+//   Opm::b200::Preconditioner<Operator>  : Dune::PreconditionerWithUpdate<X,X>
+//        what PreconditionerFactory creates for  "type": "b200dilu" | "b200ilu0"
+//        (registered with PreconditionerFactory<Op,Comm>::addCreator, PreconditionerFactory.hpp:116)
+//   Opm::b200::registerCreators<Operator, Comm>()   the addCreator calls
+//
+// Ownership: the Dune matrix and vectors stay with the caller; the handle copies the sparsity once
+// (constructor) and the values on every update() (== gpuistl/ISTLSolverGPUISTL.hpp:425-440).
+#pragma once
+
+#include "../opmb200.h"
+
+#include <cstdint>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace Opm::b200 {
+
+// ---- error conventions ---------------------------------------------------
+// OPMB200_* status -> the exception type the reference throws in the same situation.
+// MatrixBlockErrorT / SolverAbortT default to the Dune types when dune-istl is present.
+template <class MatrixBlockErrorT, class SolverAbortT>
+inline void throwOnError(int status)
+{
+    if (status == OPMB200_SUCCESS)
+        return;
+    const std::string msg = opmb200_last_error();
+    switch (status) {
+    case OPMB200_INVALID_ARGUMENT:
+    case OPMB200_BAD_OPTIONS:
+        throw std::invalid_argument(msg); // PreconditionerFactory_impl.hpp:98-106, FlexibleSolver_impl.hpp:326-329
+    case OPMB200_MATRIX_BLOCK_ERROR:
+    case OPMB200_DIAGONAL_MISSING:
+        throw MatrixBlockErrorT(msg); // rethrown untouched by ISTLSolver::prepare (ISTLSolver.hpp:394-400)
+    case OPMB200_SOLVER_ABORT:
+        throw SolverAbortT(msg); // derives from Dune::ISTLError -> "Time step too large" chop
+    default:
+        throw std::runtime_error(msg); // like OPM_GPU_SAFE_CALL
+    }
+}
+
+// ---- sparsity extraction (== gpuistl GpuSparseMatrix::extractSparsityPattern, GpuSparseMatrix.cpp:113-144)
+template <class Matrix>
+inline void extractSparsityPattern(const Matrix& A, std::vector<std::int32_t>& rowptr, std::vector<std::int32_t>& colidx)
+{
+    rowptr.assign(1, 0);
+    colidx.clear();
+    colidx.reserve(A.nonzeroes());
+    for (auto row = A.begin(); row != A.end(); ++row) {
+        for (auto col = row->begin(); col != row->end(); ++col)
+            colidx.push_back(static_cast<std::int32_t>(col.index()));
+        rowptr.push_back(static_cast<std::int32_t>(colidx.size()));
+    }
+}
+
+// one device handle shared by the operator-facing solver and the preconditioner view
+template <class Matrix>
+class Handle
+{
+public:
+    using block_type = typename Matrix::block_type;
+    static constexpr int blocksize = block_type::rows;
+
+    // serial
+    Handle(const Matrix& A, const std::string& jsonOptions)
+        : Handle(A, jsonOptions, A.N(), nullptr, nullptr)
+    {
+    }
+    // parallel: interiorSize owner rows first (ISTLSolver.hpp:299-306), NCCL communicator + halo lists
+    Handle(const Matrix& A, const std::string& jsonOptions, std::size_t interiorSize, opmb200_comm* comm,
+           const opmb200_halo* halo)
+        : A_(&A)
+    {
+        std::vector<std::int32_t> rowptr, colidx;
+        extractSparsityPattern(A, rowptr, colidx);
+        check(opmb200_create(jsonOptions.empty() ? nullptr : jsonOptions.c_str(), blocksize,
+                             static_cast<std::int64_t>(A.N()), static_cast<std::int64_t>(colidx.size()), rowptr.data(),
+                             colidx.data(), static_cast<std::int64_t>(interiorSize), comm, halo, &h_));
+        update();
+    }
+    ~Handle() { opmb200_destroy(h_); }
+    Handle(const Handle&) = delete;
+    Handle& operator=(const Handle&) = delete;
+
+    // values are contiguous from &A[0][0][0][0] (relied on at gpuistl/GpuSparseMatrix.cpp:164-167)
+    void update() { check(opmb200_update_values(h_, &(*A_)[0][0][0][0])); }
+    opmb200_solver* get() const { return h_; }
+    const Matrix& matrix() const { return *A_; }
+
+    static void check(int status);
+
+private:
+    const Matrix* A_;
+    opmb200_solver* h_ = nullptr;
+};
+
+#ifndef OPMB200_MATRIX_BLOCK_ERROR_T
+#define OPMB200_MATRIX_BLOCK_ERROR_T Dune::MatrixBlockError
+#endif
+#ifndef OPMB200_SOLVER_ABORT_T
+#define OPMB200_SOLVER_ABORT_T Dune::SolverAbort
+#endif
+
+template <class Matrix>
+void Handle<Matrix>::check(int status)
+{
+    throwOnError<OPMB200_MATRIX_BLOCK_ERROR_T, OPMB200_SOLVER_ABORT_T>(status);
+}
+
+// Dune::PreconditionerWithUpdate<X,Y> (PreconditionerWithUpdate.hpp:32-41)
+template <class Operator>
+class Preconditioner : public Dune::PreconditionerWithUpdate<typename Operator::domain_type, typename Operator::range_type>
+{
+public:
+    using X = typename Operator::domain_type;
+    using Y = typename Operator::range_type;
+    using Matrix = typename Operator::matrix_type;
+
+    explicit Preconditioner(std::shared_ptr<Handle<Matrix>> h)
+        : h_(std::move(h))
+    {
+    }
+    void pre(X&, Y&) override {}
+    void post(X&) override {}
+    // v = M^-1 d, including the BlockPreconditioner halo copy in parallel
+    void apply(X& v, const Y& d) override
+    {
+        Handle<Matrix>::check(opmb200_precond_apply(h_->get(), &v[0][0], &d[0][0]));
+    }
+    void update() override { h_->update(); }
+    bool hasPerfectUpdate() const override { return true; } // DILU.hpp:165, ParallelOverlappingILU0.hpp:147-149
+    Dune::SolverCategory::Category category() const override { return Dune::SolverCategory::sequential; }
+
+private:
+    std::shared_ptr<Handle<Matrix>> h_;
+};
+
+// Dune::InverseOperator<X,X>: BiCGSTAB + ILU0/DILU entirely on the device
+template <class Operator>
+class Solver : public Dune::InverseOperator<typename Operator::domain_type, typename Operator::range_type>
+{
+public:
+    using X = typename Operator::domain_type;
+    using Matrix = typename Operator::matrix_type;
+
+    // `jsonOptions`: the FlexibleSolver property tree as JSON (prm.write_json); see opmb200_create
+    Solver(const Operator& op, const std::string& jsonOptions)
+        : h_(std::make_shared<Handle<Matrix>>(op.getmat(), jsonOptions))
+        , prec_(std::make_shared<Preconditioner<Operator>>(h_))
+    {
+    }
+    Solver(const Operator& op, const std::string& jsonOptions, std::size_t interiorSize, opmb200_comm* comm,
+           const opmb200_halo* halo)
+        : h_(std::make_shared<Handle<Matrix>>(op.getmat(), jsonOptions, interiorSize, comm, halo))
+        , prec_(std::make_shared<Preconditioner<Operator>>(h_))
+    {
+    }
+
+    void apply(X& x, X& b, Dune::InverseOperatorResult& res) override { apply(x, b, -1.0, res); }
+
+    void apply(X& x, X& b, double reduction, Dune::InverseOperatorResult& res) override
+    {
+        opmb200_result r {};
+        const int status = opmb200_solve(h_->get(), &x[0][0], &b[0][0], reduction, &r);
+        res.iterations = r.iterations;
+        res.reduction = r.reduction;
+        res.converged = r.converged != 0;
+        res.conv_rate = r.conv_rate;
+        res.elapsed = r.elapsed;
+        Handle<Matrix>::check(status);
+    }
+
+    Dune::SolverCategory::Category category() const override { return Dune::SolverCategory::sequential; }
+    // FlexibleSolver::preconditioner(): ISTLSolver calls .update() on it every Newton step
+    Dune::PreconditionerWithUpdate<X, X>& preconditioner() { return *prec_; }
+    std::shared_ptr<Handle<Matrix>> handle() const { return h_; }
+
+private:
+    std::shared_ptr<Handle<Matrix>> h_;
+    std::shared_ptr<Preconditioner<Operator>> prec_;
+};
+
+// PreconditionerFactory<Operator,Comm>::addCreator(...) for the stand-alone preconditioner use
+// (e.g. as CPR fine smoother).  Factory is a template parameter so that this header does not
+// depend on opm-simulators' own headers.
+template <class Factory, class Operator>
+inline void registerCreators()
+{
+    using Matrix = typename Operator::matrix_type;
+    auto make = [](const char* type) {
+        return [type](const Operator& op, const auto& prm, const auto& /*weights*/, std::size_t /*pressureIndex*/) {
+            std::ostringstream js;
+            js << "{\"preconditioner\": {\"type\": \"" << type << "\", \"relaxation\": \""
+               << prm.template get<double>("relaxation", 1.0) << "\"}}";
+            auto h = std::make_shared<Handle<Matrix>>(op.getmat(), js.str());
+            return std::shared_ptr<Dune::PreconditionerWithUpdate<typename Operator::domain_type,
+                                                                  typename Operator::range_type>>(
+                std::make_shared<Preconditioner<Operator>>(h));
+        };
+    };
+    Factory::addCreator("b200dilu", make("dilu"));
+    Factory::addCreator("b200ilu0", make("ilu0"));
+}
+
+} // namespace Opm::b200

@@ -1,0 +1,40 @@
+"""world_size-2 tests: `gloo` on CPU for the host logic of the N>1 path, NCCL on >= 2 GPUs for the
+halo exchange / all-reduce / block-Jacobi path (skipped on a single-GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from conftest import ROOT
+
+WORKER = os.path.join(ROOT, "tests", "mgpu_worker.py")
+
+
+def launch(nproc, extra, port):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), WORKER] + extra
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+
+
+def test_two_rank_host_logic_gloo():
+    r = launch(2, ["--mode", "cpu"], 29611)
+    assert r.returncode == 0 and "MGPU_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def _ngpu():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec,b", [("dilu", 3), ("ilu0", 3), ("dilu", 4)])
+def test_two_rank_nccl_block_jacobi(prec, b):
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = launch(2, ["--mode", "gpu", "--prec", prec, "--b", str(b)], 29620 + b)
+    assert r.returncode == 0 and "MGPU_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
