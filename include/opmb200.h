@@ -93,6 +93,10 @@ typedef struct opmb200_info {
     double t_update_ms;    /* device time of the last update_values (H2D + relayout + factorise)   */
     double t_solve_ms;     /* device time of the last solve                                        */
     int64_t kernel_launches; /* kernels launched by this handle so far                             */
+    int schedule;          /* 0 level-scheduled sweeps, 1 chunked wavefronts                       */
+    int n_chunks;          /* chunks of the chunked schedule                                       */
+    int chunk_rows;        /* rows per chunk (chosen by the analysis when not given)               */
+    double est_steps;      /* analysis estimate of the sweep length in local steps                 */
 } opmb200_info;
 
 /* ---- library ------------------------------------------------------------------------------ */

@@ -37,7 +37,8 @@ class Info(C.Structure):
                 ("n_levels", C.c_int), ("n_slices", C.c_int), ("padded_blocks", C.c_int64),
                 ("structurally_symmetric", C.c_int), ("preconditioner", C.c_int), ("relaxation", C.c_double),
                 ("tol", C.c_double), ("maxiter", C.c_int), ("n_ranks", C.c_int), ("t_analysis_s", C.c_double),
-                ("t_update_ms", C.c_double), ("t_solve_ms", C.c_double), ("kernel_launches", C.c_int64)]
+                ("t_update_ms", C.c_double), ("t_solve_ms", C.c_double), ("kernel_launches", C.c_int64),
+                ("schedule", C.c_int), ("n_chunks", C.c_int), ("chunk_rows", C.c_int), ("est_steps", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -77,8 +77,109 @@ void partition_simple(int32_t num_cells, int32_t num_domains, int32_t* part)
             part[c] = d;
 }
 
+namespace {
+// Group ids of the "chunks" schedule for a given chunk size, plus a dataflow estimate of the sweep
+// length in units of one local step (an external dependency costs `t_ext` steps).
+struct ChunkPlan {
+    std::vector<int32_t> grp;      // group id per row
+    std::vector<int32_t> grp_chunk; // chunk of every group
+    int32_t n_groups = 0;
+    int32_t n_chunks = 0;
+    double est_steps = 0;
+    double total_steps = 0;
+};
+
+template <class RowBegin, class RowEnd>
+void plan_chunks(int64_t n, int64_t n_interior, const int32_t* col, const std::vector<int32_t>& glev,
+                 RowBegin row_begin, RowEnd row_end, int64_t R, double t_ext, ChunkPlan& P)
+{
+    // A chunk is a contiguous run of rows of the natural ordering.  It ends after R rows, at the
+    // owner/ghost border, and wherever the wavefront restarts: a row whose global level lies below
+    // the level of the chunk's first row could have started before this chunk did, so queueing it
+    // behind the chunk would serialise independent work (on a box grid: the first row of the next
+    // plane behind the last strip of the current plane).
+    std::vector<int32_t> chunk_id(n);
+    {
+        int32_t c = -1;
+        int64_t begin = 0;
+        for (int64_t i = 0; i < n; ++i) {
+            if (i == 0 || i - begin >= R || i == n_interior || glev[i] < glev[begin]) {
+                ++c;
+                begin = i;
+            }
+            chunk_id[i] = c;
+        }
+        P.n_chunks = c + 1;
+    }
+    auto chunk_of = [&](int64_t i) { return (int64_t)chunk_id[i]; };
+    std::vector<int32_t> llev(n, 0);
+    for (int64_t r = 0; r < n; ++r) {
+        const int64_t cr = chunk_of(r);
+        for (int64_t k = row_begin(r); k < row_end(r); ++k) {
+            const int32_t c = col[k];
+            if (c < r && chunk_of(c) == cr)
+                llev[r] = std::max(llev[r], llev[c] + 1);
+        }
+        for (int64_t k = row_begin(r); k < row_end(r); ++k) {
+            const int32_t c = col[k];
+            if (c > r && chunk_of(c) == cr)
+                llev[c] = std::max(llev[c], llev[r] + 1);
+        }
+    }
+    std::vector<int32_t> nl(P.n_chunks + 1, 0);
+    for (int64_t i = 0; i < n; ++i)
+        nl[chunk_of(i) + 1] = std::max(nl[chunk_of(i) + 1], llev[i] + 1);
+    for (int32_t c = 0; c < P.n_chunks; ++c)
+        nl[c + 1] += nl[c];
+    P.n_groups = nl[P.n_chunks];
+    P.grp.resize(n);
+    P.grp_chunk.assign(P.n_groups, 0);
+    std::vector<int32_t> width(P.n_groups, 0);
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t g = nl[chunk_of(i)] + llev[i];
+        P.grp[i] = g;
+        P.grp_chunk[g] = (int32_t)chunk_of(i);
+        ++width[g];
+    }
+    // Dataflow estimate of the lower sweep: a group starts when the previous group of its chunk is
+    // done and its external dependencies (rows of earlier chunks) have arrived.  Chunks are
+    // evaluated in order, which is a valid evaluation order because external producers always
+    // belong to earlier chunks.
+    std::vector<double> done(P.n_groups, 0.0);
+    double total = 0, tmax = 0;
+    // bucket rows by group
+    std::vector<int32_t> gptr(P.n_groups + 1, 0), grows(n);
+    for (int64_t i = 0; i < n; ++i)
+        ++gptr[P.grp[i] + 1];
+    for (int32_t g = 0; g < P.n_groups; ++g)
+        gptr[g + 1] += gptr[g];
+    {
+        std::vector<int32_t> cur(gptr.begin(), gptr.end() - 1);
+        for (int64_t i = 0; i < n; ++i)
+            grows[cur[P.grp[i]]++] = (int32_t)i;
+    }
+    for (int32_t g = 0; g < P.n_groups; ++g) {
+        double start = (g > 0 && P.grp_chunk[g - 1] == P.grp_chunk[g]) ? done[g - 1] : 0.0;
+        for (int32_t t = gptr[g]; t < gptr[g + 1]; ++t) {
+            const int64_t r = grows[t];
+            for (int64_t k = row_begin(r); k < row_end(r); ++k) {
+                const int32_t c = col[k];
+                if (c < r && P.grp_chunk[P.grp[c]] != P.grp_chunk[g])
+                    start = std::max(start, done[P.grp[c]] + t_ext);
+            }
+        }
+        const double cost = (width[g] + kSlice - 1) / kSlice;
+        done[g] = start + cost;
+        total += cost;
+        tmax = std::max(tmax, done[g]);
+    }
+    P.est_steps = tmax;
+    P.total_steps = total;
+}
+} // namespace
+
 int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const int32_t* col, int64_t n_interior,
-                 bool want_ilu0, Layout& L, std::string& err)
+                 bool want_ilu0, int schedule_mode, int chunk_rows, Layout& L, std::string& err)
 {
     if (b < 1 || b > 4) {
         err = "block size must be 1..4";
@@ -151,11 +252,65 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
         }
     }
     L.symmetric = symmetric;
+    L.schedule_mode = schedule_mode;
     int32_t nlev = 0;
     for (int64_t i = 0; i < n; ++i)
         nlev = std::max(nlev, lev[i] + 1);
     if (n == 0)
         nlev = 0;
+    std::vector<int32_t> grp_chunk;
+    if (schedule_mode == 1 && n > 0) {
+        // chunk size: given, or the candidate with the shortest estimated sweep (critical path of
+        // the chunk dataflow, or total work over the ~1184 chunks a B200 keeps resident)
+        ChunkPlan best;
+        const double t_ext = 4.0, resident = 1184.0;
+        std::vector<int64_t> cands;
+        if (chunk_rows > 0) {
+            cands.push_back(chunk_rows);
+        } else {
+            // "line length" of the ordering = the most frequent lower offset larger than 1 (nx on a
+            // box grid): chunks of 32 lines fill the 32 lanes of a slice best
+            std::vector<int64_t> offs;
+            const int64_t stride = std::max<int64_t>(1, n_interior / 200000);
+            for (int64_t r = 0; r < n_interior; r += stride)
+                for (int64_t k = row_begin(r); k < row_end(r); ++k)
+                    if (col[k] < r - 1)
+                        offs.push_back(r - col[k]);
+            std::sort(offs.begin(), offs.end());
+            int64_t line = 0, bestc = 0;
+            for (size_t i = 0; i < offs.size();) {
+                size_t j = i;
+                while (j < offs.size() && offs[j] == offs[i])
+                    ++j;
+                // prefer the smallest frequent offset: a plane offset is as frequent as a line offset
+                if ((int64_t)(j - i) > bestc + bestc / 4) {
+                    bestc = (int64_t)(j - i);
+                    line = offs[i];
+                }
+                i = j;
+            }
+            for (int64_t R : {(int64_t)1024, (int64_t)2048, (int64_t)4096, (int64_t)8192, 16 * line, 32 * line, 64 * line})
+                if (R >= 256 && R <= 65536 && std::find(cands.begin(), cands.end(), R) == cands.end())
+                    cands.push_back(R);
+        }
+        double best_cost = -1;
+        for (int64_t R : cands) {
+            ChunkPlan P;
+            plan_chunks(n, n_interior, col, lev, row_begin, row_end, R, t_ext, P);
+            const double padding = P.total_steps * kSlice / (double)std::max<int64_t>(n, 1);
+            const double cost = std::max(P.est_steps, P.total_steps / resident) + 200.0 * std::max(0.0, padding - 1.6);
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                best = std::move(P);
+                L.chunk_rows = (int)R;
+            }
+        }
+        lev = best.grp; // group id replaces the level from here on
+        nlev = best.n_groups;
+        grp_chunk = best.grp_chunk;
+        L.n_chunks = best.n_chunks;
+        L.est_steps = best.est_steps;
+    }
     L.n_levels = nlev;
     L.level_q0.assign(nlev + 1, 0);
     for (int64_t i = 0; i < n; ++i)
@@ -186,6 +341,13 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
     }
     L.level_slice0[nlev] = (int32_t)L.slice_level.size();
     L.n_slices = (int)L.slice_level.size();
+    if (schedule_mode == 1) {
+        L.chunk_slice0.assign(L.n_chunks + 1, 0);
+        for (int32_t g = 0; g < nlev; ++g) // groups are ordered by chunk
+            L.chunk_slice0[grp_chunk[g] + 1] = L.level_slice0[g + 1];
+        for (int32_t c = 0; c < L.n_chunks; ++c)
+            L.chunk_slice0[c + 1] = std::max(L.chunk_slice0[c + 1], L.chunk_slice0[c]);
+    }
     L.slice_q0.push_back((int32_t)n);
     L.slice_wl.assign(L.n_slices, 0);
     L.slice_wu.assign(L.n_slices, 0);

@@ -56,8 +56,10 @@ __device__ __forceinline__ void st_relaxed(double* p, double v)
 {
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
-// weak load that bypasses the L1 (always served by the L2, the point of coherence); unlike the
-// .relaxed.gpu form several of these can be in flight per thread
+// weak L1-bypassing load.  NOT usable for the dependency polls: a weak 64-bit load that races with
+// the producer's store may return a torn value (observed: a NaN that is neither the sentinel nor
+// the final value when producer and consumer share an SM), so every poll is a strong
+// ld.relaxed.gpu.
 __device__ __forceinline__ double ld_cg(const double* p)
 {
     double v;
@@ -890,18 +892,14 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                 if (cj[s] >= 0)
                     pending |= 1u << s;
             while (pending) {
-                // All outstanding dependencies are sampled with ONE round trip to the L2.  The polls
-                // are weak L1-bypassing loads (ld.global.cg): the L2 is the point of coherence, so
-                // they observe the producer's st.relaxed.gpu as soon as it lands, and -- unlike
-                // ld.relaxed.gpu, of which the hardware keeps only a few in flight per thread
-                // (scripts/microbench_hop.cu: 9 polled lines cost 3000 cycles per hop, 3 cost 1100)
-                // -- they all overlap.  Every word validates itself against the sentinel.
+                // All outstanding dependencies are sampled together with strong (ld.relaxed.gpu) loads;
+                // every word validates itself against the sentinel.
 #pragma unroll
                 for (int s = 0; s < kPrefetch; ++s)
                     if (pending & (1u << s)) {
 #pragma unroll
                         for (int r = 0; r < B; ++r)
-                            xv[s][r] = ld_cg(out + VIDX(a.n, cj[s], r));
+                            xv[s][r] = ld_relaxed(out + VIDX(a.n, cj[s], r));
                     }
 #pragma unroll
                 for (int s = 0; s < kPrefetch; ++s)
@@ -978,6 +976,325 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
 #pragma unroll
             for (int r = 0; r < B; ++r)
                 st_relaxed(out + VIDX(a.n, q, r), guard(res[r]));
+        }
+    }
+    return_ticket(a.ticket);
+}
+
+// -------------------------------------------------------------------------------------------------
+// chunked-wavefront sweeps (schedule mode "chunks")
+//
+// A producer->consumer hop through the L2 costs ~1000 cycles for a warp's worth of values, a hop
+// that stays inside a warp ~100.  Here ONE WARP walks ONE CHUNK (a contiguous run of rows of the
+// natural ordering, its rows ordered by chunk-local level) slice after slice: dependencies on rows
+// of the same chunk are served from a shared-memory ring of the last 96 results, only dependencies
+// that cross a chunk boundary are polled in the L2 (sentinel protocol as above), and those polls
+// are issued one slice ahead so that a producer that is already done costs no round trip.  The
+// matrix stream of a chunk is contiguous and is pulled into the L2 `prefetch` slices ahead with
+// bulk L2 prefetches, which turns every demand load into an L2 hit.
+// -------------------------------------------------------------------------------------------------
+constexpr int kChunkWarps = 4;
+constexpr int kRing = 128;      // ring positions per warp
+constexpr int kRingValid = 96;  // how far back the ring may be read (kRing - 32: no aliasing with writes)
+constexpr int kMetaWin = 64;    // slice metas staged in shared memory per warp
+
+struct ChunkSweepArgs {
+    int nchunks;
+    const int* chunk_slice0; // [nchunks+1]
+    const SliceMeta* slices;
+    const int* slot_col;
+    const double* M;
+    const double* dinv;
+    const double* d;
+    double* tmp;
+    double* v;
+    const int* r2n;
+    int64_t n, n_interior;
+    int ghost_zero;
+    int prefetch; // L2 prefetch distance in slices
+    Ticket ticket;
+    Scalars* sc;
+    int check_done;
+};
+
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes)
+{
+    // 16-byte aligned address and size
+    const unsigned long long a = (unsigned long long)p;
+    const unsigned long long a0 = a & ~15ull;
+    const unsigned sz = (unsigned)(((a + bytes + 15ull) & ~15ull) - a0);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(sz) : "memory");
+}
+
+template <int B, bool ILU0, bool UPPER>
+__global__ void __launch_bounds__(kChunkWarps * 32, 2) chunk_sweep_kernel(ChunkSweepArgs a)
+{
+    constexpr int BB = B * B;
+    __shared__ double ring_s[kChunkWarps][kRing * B];
+    __shared__ SliceMeta meta_s[kChunkWarps][kMetaWin];
+    const unsigned int ticket = take_ticket(a.ticket);
+    const bool skip = a.check_done && a.sc->done;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cf = (int)ticket * kChunkWarps + warp;
+    if (!skip && cf < a.nchunks) {
+        const int c = UPPER ? a.nchunks - 1 - cf : cf;
+        const int s0 = a.chunk_slice0[c], s1 = a.chunk_slice0[c + 1];
+        const int ns = s1 - s0;
+        double* ring = ring_s[warp];
+        SliceMeta* metas = meta_s[warp];
+        double* out = UPPER ? a.v : a.tmp;
+        auto slice_id = [&](int t) { return UPPER ? s1 - 1 - t : s0 + t; };
+        // metas of steps [w0, w0 + kMetaWin) live in shared memory; refilled half a window at a time
+        auto fill_meta = [&](int t_from, int cnt) {
+            for (int k = lane; k < cnt; k += 32) {
+                const int t = t_from + k;
+                if (t < ns)
+                    metas[t % kMetaWin] = a.slices[slice_id(t)];
+            }
+        };
+        fill_meta(0, kMetaWin);
+        __syncwarp();
+        const int q_lo = a.slices[s0].q0;
+        const int q_hi = a.slices[s1 - 1].q0 + a.slices[s1 - 1].count;
+
+        auto slot0 = [&](const SliceMeta& m) { return UPPER ? m.base + m.wl + 1 : m.base; };
+        auto width = [&](const SliceMeta& m) { return UPPER ? m.wu : m.wl; };
+        // is the dependency at position p served by the ring while processing a slice that starts at q0?
+        auto in_ring = [&](int p, const SliceMeta& m) {
+            return UPPER ? (p >= m.q0 + m.count && p < m.q0 + m.count + kRingValid && p < q_hi)
+                         : (p < m.q0 && p >= m.q0 - kRingValid && p >= q_lo);
+        };
+        auto load_cols = [&](int t, int (&cj)[kPrefetch]) {
+#pragma unroll
+            for (int s = 0; s < kPrefetch; ++s)
+                cj[s] = -1;
+            if (t < ns) {
+                const SliceMeta m = metas[t % kMetaWin];
+                if (lane < m.count) {
+#pragma unroll
+                    for (int s = 0; s < kPrefetch; ++s)
+                        if (s < width(m))
+                            cj[s] = __ldg(a.slot_col + (size_t)(slot0(m) + s) * 32 + lane);
+                }
+            }
+        };
+        // speculative loads of the values that do not come from the ring
+        auto load_ext = [&](int t, const int (&cj)[kPrefetch], double (&ext)[kPrefetch][B]) {
+            if (t < ns) {
+                const SliceMeta m = metas[t % kMetaWin];
+#pragma unroll
+                for (int s = 0; s < kPrefetch; ++s)
+                    if (cj[s] >= 0 && !in_ring(cj[s], m)) {
+#pragma unroll
+                        for (int r = 0; r < B; ++r)
+                            ext[s][r] = ld_relaxed(out + VIDX(a.n, cj[s], r));
+                    }
+            }
+        };
+
+        int cjA[kPrefetch], cjB[kPrefetch], cjC[kPrefetch];
+        double extA[kPrefetch][B], extB[kPrefetch][B];
+        load_cols(0, cjA);
+        load_cols(1, cjB);
+        load_ext(0, cjA, extA);
+        // warm the L2 for the first slices
+        for (int t = lane; t < min(a.prefetch, ns); t += 32) {
+            const SliceMeta m = metas[t % kMetaWin];
+            if (width(m) > 0) {
+                l2_prefetch_bulk(a.M + (size_t)slot0(m) * 32 * BB, (unsigned)width(m) * 32 * BB * 8);
+                l2_prefetch_bulk(a.slot_col + (size_t)slot0(m) * 32, (unsigned)width(m) * 128);
+            }
+        }
+
+        for (int t = 0; t < ns; ++t) {
+            if (t > 0 && (t % (kMetaWin / 2)) == 0) { // refill the half window that has just been left
+                __syncwarp();
+                fill_meta(t + kMetaWin / 2, kMetaWin / 2);
+                __syncwarp();
+            }
+            const SliceMeta m = metas[t % kMetaWin];
+            const bool active = lane < m.count;
+            const int q = m.q0 + lane;
+            const int w = width(m);
+            const int sr0 = slot0(m);
+
+            // ---- demand loads of this slice (L2 hits thanks to the prefetch below) --------------------
+            double blk[kPrefetch][BB];
+#pragma unroll
+            for (int s = 0; s < kPrefetch; ++s)
+                if (cjA[s] >= 0) {
+#pragma unroll
+                    for (int e = 0; e < BB; ++e)
+                        blk[s][e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
+                }
+            double di[BB], rhs[B], yi[B];
+            bool ghost = false;
+            if (active) {
+                if (!(ILU0 && !UPPER)) {
+#pragma unroll
+                    for (int e = 0; e < BB; ++e)
+                        di[e] = __ldcs(a.dinv + (size_t)q * BB + e);
+                }
+                if (ILU0 && a.n_interior < a.n)
+                    ghost = a.r2n[q] >= a.n_interior;
+                if (!UPPER) {
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+                        rhs[r] = ghost ? (a.ghost_zero ? 0.0 : a.v[VIDX(a.n, q, r)]) : a.d[VIDX(a.n, q, r)];
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+                        st_relaxed(a.v + VIDX(a.n, q, r), sentinel());
+                } else {
+#pragma unroll
+                    for (int r = 0; r < B; ++r) {
+                        yi[r] = a.tmp[VIDX(a.n, q, r)];
+                        rhs[r] = (ILU0) ? yi[r] : 0.0;
+                    }
+                }
+            }
+            // ---- look ahead: columns of slice t+2, speculative dependency values of slice t+1 -----------
+            load_cols(t + 2, cjC);
+            load_ext(t + 1, cjB, extB);
+            if (lane == 0 && t + a.prefetch < ns) {
+                const SliceMeta mp = metas[(t + a.prefetch) % kMetaWin];
+                if (width(mp) > 0) {
+                    l2_prefetch_bulk(a.M + (size_t)slot0(mp) * 32 * BB, (unsigned)width(mp) * 32 * BB * 8);
+                    l2_prefetch_bulk(a.slot_col + (size_t)slot0(mp) * 32, (unsigned)width(mp) * 128);
+                }
+                if (!(ILU0 && !UPPER))
+                    l2_prefetch_bulk(a.dinv + (size_t)mp.q0 * BB, (unsigned)mp.count * BB * 8);
+                const double* in = UPPER ? a.tmp : a.d;
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    l2_prefetch_bulk(in + VIDX(a.n, mp.q0, r), (unsigned)mp.count * 8);
+            }
+
+            // ---- dependencies: ring (same chunk, recent) or L2 (other chunks) ---------------------------
+            if (active) {
+                double xv[kPrefetch][B];
+                unsigned pending = 0;
+#pragma unroll
+                for (int s = 0; s < kPrefetch; ++s)
+                    if (cjA[s] >= 0) {
+                        if (in_ring(cjA[s], m)) {
+#pragma unroll
+                            for (int r = 0; r < B; ++r)
+                                xv[s][r] = ring[r * kRing + (cjA[s] & (kRing - 1))];
+                        } else {
+                            bool ok = true;
+#pragma unroll
+                            for (int r = 0; r < B; ++r) {
+                                xv[s][r] = extA[s][r];
+                                ok = ok && !is_sentinel(xv[s][r]);
+                            }
+                            if (!ok)
+                                pending |= 1u << s;
+                        }
+                    }
+                while (pending) {
+#pragma unroll
+                    for (int s = 0; s < kPrefetch; ++s)
+                        if (pending & (1u << s)) {
+#pragma unroll
+                            for (int r = 0; r < B; ++r)
+                                xv[s][r] = ld_relaxed(out + VIDX(a.n, cjA[s], r));
+                        }
+#pragma unroll
+                    for (int s = 0; s < kPrefetch; ++s)
+                        if (pending & (1u << s)) {
+                            bool ok = true;
+#pragma unroll
+                            for (int r = 0; r < B; ++r)
+                                ok = ok && !is_sentinel(xv[s][r]);
+                            if (ok)
+                                pending &= ~(1u << s);
+                        }
+                }
+#pragma unroll
+                for (int s = 0; s < kPrefetch; ++s)
+                    if (cjA[s] >= 0) {
+                        if (UPPER && !ILU0)
+                            blk_umv<B>(blk[s], xv[s], rhs);
+                        else
+                            blk_mmv<B>(blk[s], xv[s], rhs);
+                    }
+                for (int s = kPrefetch; s < w; ++s) { // rows wider than the register window
+                    const int cc = __ldg(a.slot_col + (size_t)(sr0 + s) * 32 + lane);
+                    if (cc < 0)
+                        continue;
+                    double bl[BB], xs[B];
+#pragma unroll
+                    for (int e = 0; e < BB; ++e)
+                        bl[e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
+                    if (in_ring(cc, m)) {
+#pragma unroll
+                        for (int r = 0; r < B; ++r)
+                            xs[r] = ring[r * kRing + (cc & (kRing - 1))];
+                    } else {
+                        bool ok;
+                        do {
+                            ok = true;
+#pragma unroll
+                            for (int r = 0; r < B; ++r) {
+                                xs[r] = ld_relaxed(out + VIDX(a.n, cc, r));
+                                ok = ok && !is_sentinel(xs[r]);
+                            }
+                        } while (!ok);
+                    }
+                    if (UPPER && !ILU0)
+                        blk_umv<B>(bl, xs, rhs);
+                    else
+                        blk_mmv<B>(bl, xs, rhs);
+                }
+            }
+            // ---- finish the rows, publish to the ring and to memory -------------------------------------
+            double res[B];
+            if (active) {
+                if (!UPPER) {
+                    if (ILU0) {
+#pragma unroll
+                        for (int r = 0; r < B; ++r)
+                            res[r] = rhs[r];
+                    } else {
+                        blk_mv<B>(di, rhs, res);
+                    }
+                } else if (ILU0) {
+                    if (ghost) {
+#pragma unroll
+                        for (int r = 0; r < B; ++r)
+                            res[r] = rhs[r];
+                    } else {
+                        blk_mv<B>(di, rhs, res);
+                    }
+                } else {
+                    blk_mmv<B>(di, rhs, yi);
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+                        res[r] = yi[r];
+                }
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    res[r] = guard(res[r]);
+            }
+            __syncwarp(); // every lane has finished reading the ring
+            if (active) {
+#pragma unroll
+                for (int r = 0; r < B; ++r) {
+                    ring[r * kRing + (q & (kRing - 1))] = res[r];
+                    st_relaxed(out + VIDX(a.n, q, r), res[r]);
+                    if (UPPER)
+                        a.tmp[VIDX(a.n, q, r)] = sentinel();
+                }
+            }
+            __syncwarp(); // ring writes visible to the whole warp before the next slice
+#pragma unroll
+            for (int s = 0; s < kPrefetch; ++s) {
+                cjA[s] = cjB[s];
+                cjB[s] = cjC[s];
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    extA[s][r] = extB[s][r];
+            }
         }
     }
     return_ticket(a.ticket);

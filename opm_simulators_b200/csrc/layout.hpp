@@ -33,10 +33,21 @@ struct Layout {
     // reference-exact artefacts (what the parity tests compare bit for bit)
     std::vector<int32_t> ref_level_rows, ref_level_ptr; // getMatrixRowColoring(A, LOWER)
 
-    // schedule (level sets of pattern(A) U pattern(A^T); identical to the above when symmetric)
-    int n_levels = 0;
-    std::vector<int32_t> level_q0; // [n_levels+1] first position of each level
+    // schedule groups: rows of one group are mutually independent and depend only on rows of
+    // earlier groups (lower sweep) / later groups (upper sweep).
+    //   mode 0 "levels": group = level of pattern(A) U pattern(A^T) (== the reference level sets
+    //                    when the pattern is structurally symmetric)
+    //   mode 1 "chunks": rows are cut into contiguous chunks of the natural ordering, group =
+    //                    (chunk, level inside the chunk); one warp walks one chunk, so only
+    //                    dependencies that cross a chunk boundary travel through the L2
+    int schedule_mode = 0;
+    int chunk_rows = 0;
+    int n_levels = 0;              // number of groups
+    std::vector<int32_t> level_q0; // [n_levels+1] first position of each group
     std::vector<int32_t> r2n, n2r; // position <-> natural row
+    int n_chunks = 0;
+    std::vector<int32_t> chunk_slice0; // [n_chunks+1] (mode 1)
+    double est_steps = 0;              // schedule estimate of the chosen chunking (mode 1)
 
     // slices
     int n_slices = 0;
@@ -66,8 +77,9 @@ int row_coloring(int64_t n, const int32_t* rowptr, const int32_t* col, int type,
                  int32_t* level_rows, int32_t* level_ptr);
 
 // Builds everything above.  Returns 0 or an opmb200_status (diagonal missing, bad arguments).
+// schedule_mode: 0 levels, 1 chunks; chunk_rows: rows per chunk (<= 0: chosen automatically)
 int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const int32_t* col, int64_t n_interior,
-                 bool want_ilu0, Layout& L, std::string& err);
+                 bool want_ilu0, int schedule_mode, int chunk_rows, Layout& L, std::string& err);
 
 void partition_simple(int32_t num_cells, int32_t num_domains, int32_t* part);
 

@@ -118,6 +118,10 @@ struct opmb200_solver {
     int verbosity = 0;
     int op_repeats = 1;
     int throttle = 3;
+    int schedule = 0;   // 0 levels, 1 chunks
+    int chunk_rows = 0; // <= 0: automatic
+    int prefetch = 12;  // L2 prefetch distance of the chunk sweeps, in slices
+    int debug_lower_only = 0;
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -126,7 +130,7 @@ struct opmb200_solver {
     int epoch = 0;
 
     DevBuf<SliceMeta> slices;
-    DevBuf<int> slot_col, slot_src, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag;
+    DevBuf<int> slot_col, slot_src, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag, chunk_slice0;
     DevBuf<double> A, F, dinv, vals_native;
     DevBuf<double> vx, vr, vp, vv, vt, vy, vrt, vtmp, vw, nat0, nat1;
     DevBuf<double> partials, hist, sums, dot_out;
@@ -314,6 +318,37 @@ SweepArgs sweep_args(opmb200_solver* s, const double* d, double* v, int ghost_ze
 
 int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
 {
+    if (s->schedule == 1) { // chunked wavefronts: one warp per chunk
+        ChunkSweepArgs c;
+        c.nchunks = s->L.n_chunks;
+        c.chunk_slice0 = s->chunk_slice0.p;
+        c.slices = a.slices;
+        c.slot_col = a.slot_col;
+        c.M = a.M;
+        c.dinv = a.dinv;
+        c.d = a.d;
+        c.tmp = a.tmp;
+        c.v = a.v;
+        c.r2n = a.r2n;
+        c.n = a.n;
+        c.n_interior = a.n_interior;
+        c.ghost_zero = a.ghost_zero;
+        c.prefetch = s->prefetch;
+        c.ticket = a.ticket;
+        c.sc = a.sc;
+        c.check_done = a.check_done;
+        const int cgrid = std::max(1, (s->L.n_chunks + kChunkWarps - 1) / kChunkWarps);
+        DISPATCH_B(s->b, {
+            if (s->prec == PREC_ILU0) {
+                if (upper) chunk_sweep_kernel<B, true, true><<<cgrid, kChunkWarps * 32, 0, s->stream>>>(c);
+                else chunk_sweep_kernel<B, true, false><<<cgrid, kChunkWarps * 32, 0, s->stream>>>(c);
+            } else {
+                if (upper) chunk_sweep_kernel<B, false, true><<<cgrid, kChunkWarps * 32, 0, s->stream>>>(c);
+                else chunk_sweep_kernel<B, false, false><<<cgrid, kChunkWarps * 32, 0, s->stream>>>(c);
+            }
+        });
+        return check_launch(s, upper ? "upper chunk sweep" : "lower chunk sweep");
+    }
     const int grid = s->slice_grid();
     DISPATCH_B(s->b, {
         if (s->prec == PREC_ILU0) {
@@ -336,6 +371,11 @@ int prec_apply(opmb200_solver* s, const double* d, double* v, int ghost_zero, in
     }
     const SweepArgs a = sweep_args(s, d, v, ghost_zero, check_done);
     TRY(launch_sweep(s, a, false));
+    if (s->debug_lower_only) { // test hook: expose the intermediate y of the lower sweep
+        CUDA_TRY(cudaMemcpyAsync(v, s->vtmp.p, s->len() * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
+        fill_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->vtmp.p, s->len(), sentinel_host());
+        return check_launch(s, "fill");
+    }
     TRY(launch_sweep(s, a, true));
     TRY(copy_owner_to_all(s, v));
     if (s->prec == PREC_ILU0 && std::abs(s->relaxation - 1.0) > 1e-15) {
@@ -445,6 +485,13 @@ int parse_options(opmb200_solver* s, const char* json)
         s->relaxation = prm.get<double>("preconditioner.relaxation", 1.0);
         s->op_repeats = prm.get<int>("b200.operator_repeats", 1);
         s->throttle = prm.get<int>("b200.throttle_levels", 3);
+        const std::string sched = prm.get<std::string>("b200.schedule", "levels");
+        if (sched != "levels" && sched != "chunks")
+            return fail(OPMB200_BAD_OPTIONS, "b200.schedule must be \"levels\" or \"chunks\"");
+        s->schedule = sched == "chunks" ? 1 : 0;
+        s->chunk_rows = prm.get<int>("b200.chunk_rows", 0);
+        s->prefetch = std::max(1, std::min(24, prm.get<int>("b200.prefetch_slices", 12)));
+        s->debug_lower_only = prm.get<int>("b200.debug_lower_only", 0);
     } catch (const std::exception& e) {
         return fail(OPMB200_BAD_OPTIONS, e.what());
     }
@@ -694,7 +741,8 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
     TRY(parse_options(s.get(), json_options));
     const auto t0 = std::chrono::steady_clock::now();
     std::string err;
-    const int rc = build_layout(block_size, n_rows, nnzb, rowptr, colidx, n_interior, s->prec == PREC_ILU0, s->L, err);
+    const int rc = build_layout(block_size, n_rows, nnzb, rowptr, colidx, n_interior, s->prec == PREC_ILU0, s->schedule,
+                                s->chunk_rows, s->L, err);
     if (rc != OPMB200_SUCCESS)
         return fail(rc, err);
     s->t_analysis_s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
@@ -737,6 +785,7 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
     CUDA_TRY(s->r2n.upload(L.r2n, st));
     CUDA_TRY(s->n2r.upload(L.n2r, st));
     CUDA_TRY(s->level_q0.upload(L.level_q0, st));
+    CUDA_TRY(s->chunk_slice0.upload(L.chunk_slice0, st));
     CUDA_TRY(s->l_transpose.upload(L.l_transpose, st));
     if (s->prec == PREC_ILU0) {
         CUDA_TRY(s->trip_ptr.upload(L.trip_ptr, st));
@@ -932,6 +981,10 @@ int opmb200_get_info(opmb200_solver* s, opmb200_info* info)
     info->t_update_ms = s->t_update_ms;
     info->t_solve_ms = s->t_solve_ms;
     info->kernel_launches = s->launches;
+    info->schedule = s->schedule;
+    info->n_chunks = s->L.n_chunks;
+    info->chunk_rows = s->L.chunk_rows;
+    info->est_steps = s->L.est_steps;
     return OPMB200_SUCCESS;
 }
 

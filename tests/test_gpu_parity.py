@@ -11,11 +11,28 @@ from opm_simulators_b200.flexible_solver import (FlexibleSolver, ISTLSolverB200,
                                                  NumericalProblem, SolverAbort)
 from oracle import oracle as orc
 
+import os
+
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
+# the whole file runs once per sweep schedule: OPMB200_TEST_SCHEDULE=levels|chunks (default: both via the fixture)
+
+
+_SCHEDULE = {"name": os.environ.get("OPMB200_TEST_SCHEDULE", "chunks"), "chunk_rows": 0}
+
+
+@pytest.fixture(autouse=True, params=["levels", "chunks", "chunks64"])
+def schedule(request):
+    """every test runs with the level-scheduled sweeps, the chunked wavefronts (automatic chunk size) and
+    deliberately tiny chunks (64 rows: many chunk-boundary dependencies, ring wrap-around)"""
+    _SCHEDULE["name"] = "levels" if request.param == "levels" else "chunks"
+    _SCHEDULE["chunk_rows"] = 64 if request.param == "chunks64" else 0
+    yield request.param
 
 
 def opts(prec, tol=1e-2, maxiter=200, relaxation=None, **extra):
+    extra.setdefault("b200", {})
+    extra["b200"] = dict(extra["b200"], schedule=_SCHEDULE["name"], chunk_rows=_SCHEDULE["chunk_rows"])
     p = {"type": prec}
     if relaxation is not None:
         p["relaxation"] = relaxation
@@ -49,6 +66,7 @@ def test_matr33_golden_solution(golden, b, prec):
     o = dict(golden["options_flexiblesolver_1x1"])
     o["preconditioner"] = {"type": prec}
     o["verbosity"] = "0"
+    o["b200"] = {"schedule": _SCHEDULE["name"], "chunk_rows": _SCHEDULE["chunk_rows"]}
     fs = FlexibleSolver(MatrixAdapter(A), o)
     x, rhs = np.zeros(9), np.array(golden["rhs3"])
     res = fs.apply(x, rhs)
@@ -64,7 +82,8 @@ def test_matr33rep_unpreconditioned_golden(golden, b):
     """tests/test_preconditionerfactory.cpp:231-376: plain BiCGSTAB on the RepeatingOperator A*A"""
     A = coo_to_bcsr(golden["matr33rep"], b)
     o = dict(golden["options_flexiblesolver_simple"])
-    o["b200"] = {"operator_repeats": golden["matr33rep_repeats"]}
+    o["b200"] = {"operator_repeats": golden["matr33rep_repeats"], "schedule": _SCHEDULE["name"],
+                 "chunk_rows": _SCHEDULE["chunk_rows"]}
     from opm_simulators_b200.flexible_solver import PreconditionerFactory, PreconditionerWithUpdate
     PreconditionerFactory.addCreator("nothing", lambda op, prm: PreconditionerWithUpdate(op, prm))
     fs = FlexibleSolver(MatrixAdapter(A), o)
