@@ -31,8 +31,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    if os.environ.get("OPMB200_DEBUG_PRINT"):
-        cmd += ["-DOPMB200_DEBUG_PRINT"]
+    if os.environ.get("OPMB200_PROFILE"):
+        cmd += ["-DOPMB200_PROFILE"]
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-lnccl"]
     r = subprocess.run(cmd, capture_output=True, text=True)

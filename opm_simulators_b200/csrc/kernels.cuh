@@ -92,6 +92,71 @@ __device__ __forceinline__ double guard(double v)
 // dependency polls of the sweeps alike).
 #define VIDX(n, q, c) ((size_t)(c) * (size_t)(n) + (size_t)(q))
 
+// Dependency records.  The values the sweeps hand from row to row live in arrays of one aligned
+// record per row (2 doubles for b <= 2, 4 doubles = one 32-byte sector for b = 3, 4), so that a
+// consumer samples a dependency with ONE strong vector load and a producer publishes it with ONE
+// strong vector store: the hardware keeps only a few strong loads in flight per thread
+// (scripts/microbench_hop.cu: nine polled words cost 3000 cycles per hop, three cost 1100).
+// Every word still validates itself against the sentinel, so no atomicity beyond 8 bytes is needed.
+template <int B>
+struct Rec {
+    static constexpr int W = (B <= 2) ? 2 : 4;
+};
+template <int B>
+__device__ __forceinline__ void rec_load_strong(const double* base, size_t q, double (&x)[B])
+{
+    const double* p = base + q * Rec<B>::W;
+    if constexpr (Rec<B>::W == 2) {
+        double w0, w1;
+        asm volatile("ld.relaxed.gpu.global.v2.f64 {%0,%1}, [%2];" : "=d"(w0), "=d"(w1) : "l"(p) : "memory");
+        x[0] = w0;
+        if constexpr (B == 2)
+            x[1] = w1;
+    } else {
+        double w0, w1, w2, w3;
+        asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                     : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3)
+                     : "l"(p)
+                     : "memory");
+        x[0] = w0;
+        x[1] = w1;
+        x[2] = w2;
+        if constexpr (B == 4)
+            x[3] = w3;
+    }
+}
+template <int B>
+__device__ __forceinline__ void rec_store_strong(double* base, size_t q, const double (&x)[B])
+{
+    double* p = base + q * Rec<B>::W;
+    if constexpr (Rec<B>::W == 2) {
+        const double w1 = (B == 2) ? x[B - 1] : 0.0;
+        asm volatile("st.relaxed.gpu.global.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(x[0]), "d"(w1) : "memory");
+    } else {
+        const double w3 = (B == 4) ? x[B - 1] : 0.0;
+        asm volatile("st.relaxed.gpu.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(w3)
+                     : "memory");
+    }
+}
+template <int B>
+__device__ __forceinline__ void rec_store_sentinel(double* base, size_t q)
+{
+    double x[B];
+#pragma unroll
+    for (int r = 0; r < B; ++r)
+        x[r] = __longlong_as_double((long long)kSentinelBits);
+    rec_store_strong<B>(base, q, x);
+}
+template <int B>
+__device__ __forceinline__ bool rec_valid(const double (&x)[B])
+{
+    bool ok = true;
+#pragma unroll
+    for (int r = 0; r < B; ++r)
+        ok = ok && !is_sentinel(x[r]);
+    return ok;
+}
+
 // element e of block slot (slot_row, lane)
 template <int BB>
 __device__ __forceinline__ size_t elem_index(int slot_row, int lane, int e)
@@ -653,6 +718,7 @@ struct FactorArgs {
     const int* trip_src;
     const int* trip_dst;
     double* dinv;           // [n][b*b] by position
+    double* dinv_s;         // the same in slice layout [slice][b*b][32] (what the chunk sweeps stage)
     int* row_flag;          // [n]
     int epoch;
     Ticket ticket;
@@ -708,8 +774,10 @@ __global__ void __launch_bounds__(kCtaThreads) dilu_factor_kernel(FactorArgs a)
             if (!blk_invert<B>(D))
                 a.sc->factor_error = 1;
 #pragma unroll
-            for (int e = 0; e < BB; ++e)
+            for (int e = 0; e < BB; ++e) {
                 st_relaxed(a.dinv + (size_t)q * BB + e, D[e]);
+                a.dinv_s[((size_t)S * BB + e) * 32 + lane] = D[e];
+            }
             __threadfence();
             st_relaxed(a.row_flag + q, a.epoch);
         }
@@ -774,6 +842,7 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
             for (int e = 0; e < BB; ++e) {
                 st_relaxed(a.F + elem_index<BB>(m.base + m.wl, lane, e), D[e]);
                 st_relaxed(a.dinv + (size_t)q * BB + e, D[e]);
+                a.dinv_s[((size_t)S * BB + e) * 32 + lane] = D[e];
             }
             __threadfence();
             st_relaxed(a.row_flag + q, a.epoch);
@@ -797,8 +866,9 @@ struct SweepArgs {
     const double* M;     // block values (A for DILU, F for ILU0)
     const double* dinv;  // [n][b*b]
     const double* d;     // right-hand side (lower)
-    double* tmp;         // y
-    double* v;           // result
+    double* tmp;         // y, dependency records [n][Rec<B>::W]
+    double* vpoll;       // result as dependency records (what the upper sweep's consumers poll)
+    double* v;           // result, component-major like every solver vector
     const int* level_q0; // [n_levels+1]
     int n_levels;
     int throttle;        // how many levels behind the front fine-grained polling starts
@@ -828,7 +898,7 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
         const int q = m.q0 + lane;
         const int w = UPPER ? m.wu : m.wl;
         const int sr0 = UPPER ? m.base + m.wl + 1 : m.base;
-        double* out = UPPER ? a.v : a.tmp; // what this sweep produces and what its consumers poll
+        double* out = UPPER ? a.vpoll : a.tmp; // record array this sweep produces and its consumers poll
 
         // ---- 1. prefetch everything that does not depend on other rows --------------------------
         int cj[kPrefetch];
@@ -858,15 +928,12 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
 #pragma unroll
                 for (int r = 0; r < B; ++r)
                     rhs[r] = ghost ? (a.ghost_zero ? 0.0 : a.v[VIDX(a.n, q, r)]) : a.d[VIDX(a.n, q, r)];
+                rec_store_sentinel<B>(a.vpoll, (size_t)q); // arm the upper sweep's records
+            } else {
+                rec_load_strong<B>(a.tmp, (size_t)q, yi); // y_i of the lower sweep (complete: previous kernel)
 #pragma unroll
                 for (int r = 0; r < B; ++r)
-                    st_relaxed(a.v + VIDX(a.n, q, r), sentinel()); // arm the upper sweep's output
-            } else {
-#pragma unroll
-                for (int r = 0; r < B; ++r) {
-                    yi[r] = a.tmp[VIDX(a.n, q, r)]; // y_i of the lower sweep (complete: previous kernel)
                     rhs[r] = (ILU0) ? yi[r] : 0.0;
-                }
             }
         }
 
@@ -875,7 +942,7 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
             const int lv = UPPER ? m.level + a.throttle : m.level - a.throttle;
             if (lv >= 0 && lv < a.n_levels) {
                 const int pq = UPPER ? a.level_q0[lv] : a.level_q0[lv + 1] - 1;
-                const double* pp = out + VIDX(a.n, pq, B - 1);
+                const double* pp = out + (size_t)pq * Rec<B>::W + (B - 1);
                 if (lane == 0)
                     while (is_sentinel(ld_relaxed(pp)))
                         __nanosleep(200);
@@ -892,25 +959,16 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                 if (cj[s] >= 0)
                     pending |= 1u << s;
             while (pending) {
-                // All outstanding dependencies are sampled together with strong (ld.relaxed.gpu) loads;
-                // every word validates itself against the sentinel.
+                // all outstanding dependencies are sampled together, one strong vector load each;
+                // every word validates itself against the sentinel
 #pragma unroll
                 for (int s = 0; s < kPrefetch; ++s)
-                    if (pending & (1u << s)) {
-#pragma unroll
-                        for (int r = 0; r < B; ++r)
-                            xv[s][r] = ld_relaxed(out + VIDX(a.n, cj[s], r));
-                    }
+                    if (pending & (1u << s))
+                        rec_load_strong<B>(out, (size_t)cj[s], xv[s]);
 #pragma unroll
                 for (int s = 0; s < kPrefetch; ++s)
-                    if (pending & (1u << s)) {
-                        bool ok = true;
-#pragma unroll
-                        for (int r = 0; r < B; ++r)
-                            ok = ok && !is_sentinel(xv[s][r]);
-                        if (ok)
-                            pending &= ~(1u << s);
-                    }
+                    if ((pending & (1u << s)) && rec_valid<B>(xv[s]))
+                        pending &= ~(1u << s);
             }
 #pragma unroll
             for (int s = 0; s < kPrefetch; ++s)
@@ -929,15 +987,9 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
 #pragma unroll
                 for (int e = 0; e < BB; ++e)
                     bl[e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
-                bool ok;
                 do {
-                    ok = true;
-#pragma unroll
-                    for (int r = 0; r < B; ++r) {
-                        xs[r] = ld_relaxed(out + VIDX(a.n, c, r));
-                        ok = ok && !is_sentinel(xs[r]);
-                    }
-                } while (!ok);
+                    rec_load_strong<B>(out, (size_t)c, xs);
+                } while (!rec_valid<B>(xs));
                 if (UPPER && !ILU0)
                     blk_umv<B>(bl, xs, rhs);
                 else
@@ -969,13 +1021,17 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                     for (int r = 0; r < B; ++r)
                         res[r] = yi[r];
                 }
-#pragma unroll
-                for (int r = 0; r < B; ++r)
-                    a.tmp[VIDX(a.n, q, r)] = sentinel(); // re-arm for the next apply
+                rec_store_sentinel<B>(a.tmp, (size_t)q); // re-arm for the next apply
             }
 #pragma unroll
             for (int r = 0; r < B; ++r)
-                st_relaxed(out + VIDX(a.n, q, r), guard(res[r]));
+                res[r] = guard(res[r]);
+            rec_store_strong<B>(out, (size_t)q, res);
+            if (UPPER) {
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    a.v[VIDX(a.n, q, r)] = res[r];
+            }
         }
     }
     return_ticket(a.ticket);
@@ -984,19 +1040,38 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
 // -------------------------------------------------------------------------------------------------
 // chunked-wavefront sweeps (schedule mode "chunks")
 //
-// A producer->consumer hop through the L2 costs ~1000 cycles for a warp's worth of values, a hop
-// that stays inside a warp ~100.  Here ONE WARP walks ONE CHUNK (a contiguous run of rows of the
-// natural ordering, its rows ordered by chunk-local level) slice after slice: dependencies on rows
-// of the same chunk are served from a shared-memory ring of the last 96 results, only dependencies
-// that cross a chunk boundary are polled in the L2 (sentinel protocol as above), and those polls
-// are issued one slice ahead so that a producer that is already done costs no round trip.  The
-// matrix stream of a chunk is contiguous and is pulled into the L2 `prefetch` slices ahead with
-// bulk L2 prefetches, which turns every demand load into an L2 hit.
+// A producer->consumer hop through the L2 costs 500-1000+ cycles, a hop that stays inside a warp
+// ~100.  Here ONE WARP walks ONE CHUNK (a contiguous run of rows of the natural ordering, its rows
+// ordered by chunk-local level) slice after slice:
+//   * dependencies on rows of the same chunk are served from a shared-memory ring of the last 96
+//     results; only dependencies that cross a chunk boundary are polled in the L2 (dependency
+//     records + sentinel, as above), and those polls are issued one slice ahead, so a producer
+//     that is already done costs no round trip;
+//   * the matrix stream of a chunk (block values, column positions, Dinv) is contiguous; it is
+//     pulled into a per-warp shared-memory ring of kStages slices with TMA bulk copies
+//     (cp.async.bulk -> UBLKCP) that complete on per-stage mbarriers, so no load latency is
+//     exposed inside a step: the warp only ever waits for a stage that was requested kStages-1
+//     steps earlier.
 // -------------------------------------------------------------------------------------------------
 constexpr int kChunkWarps = 4;
 constexpr int kRing = 128;      // ring positions per warp
 constexpr int kRingValid = 96;  // how far back the ring may be read (kRing - 32: no aliasing with writes)
 constexpr int kMetaWin = 64;    // slice metas staged in shared memory per warp
+
+template <int B>
+struct ChunkSmem {
+    static constexpr int BB = B * B;
+    static constexpr int kStages = (B <= 3) ? 4 : 2;
+    static constexpr int kBlkBytes = kPrefetch * 32 * BB * 8;
+    static constexpr int kDinvBytes = 32 * BB * 8;
+    static constexpr int kColBytes = kPrefetch * 32 * 4;
+    static constexpr int kStageBytes = kBlkBytes + kDinvBytes + kColBytes; // multiple of 128
+    static constexpr int kRingBytes = kRing * B * 8;
+    static constexpr int kMetaBytes = kMetaWin * (int)sizeof(SliceMeta);
+    static constexpr int kBarBytes = 64; // kStages mbarriers
+    static constexpr int kWarpBytes = kStages * kStageBytes + kRingBytes + kMetaBytes + kBarBytes;
+    static constexpr int kCtaBytes = kChunkWarps * kWarpBytes;
+};
 
 struct ChunkSweepArgs {
     int nchunks;
@@ -1004,14 +1079,15 @@ struct ChunkSweepArgs {
     const SliceMeta* slices;
     const int* slot_col;
     const double* M;
-    const double* dinv;
+    const double* dinv_s; // Dinv in slice layout [slice][b*b][32]
     const double* d;
-    double* tmp;
+    double* tmp;   // dependency records of the lower sweep's result y
+    double* vpoll; // dependency records of the upper sweep's result
     double* v;
     const int* r2n;
     int64_t n, n_interior;
     int ghost_zero;
-    int prefetch; // L2 prefetch distance in slices
+    int debug; // timing experiments only: 1 = do not wait for dependencies
     Ticket ticket;
     Scalars* sc;
     int check_done;
@@ -1019,32 +1095,79 @@ struct ChunkSweepArgs {
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes)
 {
-    // 16-byte aligned address and size
+    // cp.async.bulk.prefetch.L2 (SASS: UBLKPF.L2); address and size rounded to 16 bytes
     const unsigned long long a = (unsigned long long)p;
     const unsigned long long a0 = a & ~15ull;
     const unsigned sz = (unsigned)(((a + bytes + 15ull) & ~15ull) - a0);
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(sz) : "memory");
 }
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+// TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+#ifdef OPMB200_PROFILE
+__device__ unsigned long long g_prof[16];
+#define PROF_MARK(i)                                                                                                   \
+    do {                                                                                                               \
+        const long long now__ = clock64();                                                                             \
+        if (lane == 0)                                                                                                 \
+            atomicAdd(&g_prof[i], (unsigned long long)(now__ - tprev__));                                              \
+        tprev__ = clock64();                                                                                           \
+    } while (0)
+#else
+#define PROF_MARK(i)
+#endif
 
 template <int B, bool ILU0, bool UPPER>
-__global__ void __launch_bounds__(kChunkWarps * 32, 2) chunk_sweep_kernel(ChunkSweepArgs a)
+__global__ void __launch_bounds__(kChunkWarps * 32, 1) chunk_sweep_kernel(ChunkSweepArgs a)
 {
+    using SM = ChunkSmem<B>;
     constexpr int BB = B * B;
-    __shared__ double ring_s[kChunkWarps][kRing * B];
-    __shared__ SliceMeta meta_s[kChunkWarps][kMetaWin];
+    constexpr int NS = SM::kStages;
+    constexpr bool NEED_DINV = !(ILU0 && !UPPER);
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const unsigned int ticket = take_ticket(a.ticket);
     const bool skip = a.check_done && a.sc->done;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int cf = (int)ticket * kChunkWarps + warp;
     if (!skip && cf < a.nchunks) {
+        unsigned char* wbase = smem_raw + (size_t)warp * SM::kWarpBytes;
+        unsigned char* stage0 = wbase;
+        double* ring = reinterpret_cast<double*>(wbase + NS * SM::kStageBytes);
+        SliceMeta* metas = reinterpret_cast<SliceMeta*>(wbase + NS * SM::kStageBytes + SM::kRingBytes);
+        unsigned long long* bars
+            = reinterpret_cast<unsigned long long*>(wbase + NS * SM::kStageBytes + SM::kRingBytes + SM::kMetaBytes);
         const int c = UPPER ? a.nchunks - 1 - cf : cf;
         const int s0 = a.chunk_slice0[c], s1 = a.chunk_slice0[c + 1];
         const int ns = s1 - s0;
-        double* ring = ring_s[warp];
-        SliceMeta* metas = meta_s[warp];
-        double* out = UPPER ? a.v : a.tmp;
+        double* out = UPPER ? a.vpoll : a.tmp;
         auto slice_id = [&](int t) { return UPPER ? s1 - 1 - t : s0 + t; };
-        // metas of steps [w0, w0 + kMetaWin) live in shared memory; refilled half a window at a time
         auto fill_meta = [&](int t_from, int cnt) {
             for (int k = lane; k < cnt; k += 32) {
                 const int t = t_from + k;
@@ -1052,125 +1175,140 @@ __global__ void __launch_bounds__(kChunkWarps * 32, 2) chunk_sweep_kernel(ChunkS
                     metas[t % kMetaWin] = a.slices[slice_id(t)];
             }
         };
+        if (lane == 0)
+            for (int i = 0; i < NS; ++i)
+                mbar_init(bars + i, 1);
         fill_meta(0, kMetaWin);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         __syncwarp();
-        const int q_lo = a.slices[s0].q0;
-        const int q_hi = a.slices[s1 - 1].q0 + a.slices[s1 - 1].count;
+        const int q_lo = ns > 0 ? a.slices[s0].q0 : 0;
+        const int q_hi = ns > 0 ? a.slices[s1 - 1].q0 + a.slices[s1 - 1].count : 0;
 
         auto slot0 = [&](const SliceMeta& m) { return UPPER ? m.base + m.wl + 1 : m.base; };
         auto width = [&](const SliceMeta& m) { return UPPER ? m.wu : m.wl; };
-        // is the dependency at position p served by the ring while processing a slice that starts at q0?
         auto in_ring = [&](int p, const SliceMeta& m) {
             return UPPER ? (p >= m.q0 + m.count && p < m.q0 + m.count + kRingValid && p < q_hi)
                          : (p < m.q0 && p >= m.q0 - kRingValid && p >= q_lo);
         };
-        auto load_cols = [&](int t, int (&cj)[kPrefetch]) {
-#pragma unroll
-            for (int s = 0; s < kPrefetch; ++s)
-                cj[s] = -1;
-            if (t < ns) {
+        // request the staged part of slice t: block values and columns of its first kPrefetch slot
+        // rows, and its Dinv
+        auto request = [&](int t) {
+            if (t < ns && lane == 0) {
                 const SliceMeta m = metas[t % kMetaWin];
-                if (lane < m.count) {
-#pragma unroll
-                    for (int s = 0; s < kPrefetch; ++s)
-                        if (s < width(m))
-                            cj[s] = __ldg(a.slot_col + (size_t)(slot0(m) + s) * 32 + lane);
+                const int st = t % NS;
+                unsigned char* sb = stage0 + (size_t)st * SM::kStageBytes;
+                const int wst = min(width(m), kPrefetch);
+                const unsigned bytes = (unsigned)wst * (32 * BB * 8 + 128) + (NEED_DINV ? SM::kDinvBytes : 0);
+                if (bytes == 0) {
+                    mbar_expect_tx(bars + st, 0);
+                } else {
+                    mbar_expect_tx(bars + st, bytes);
+                    if (wst > 0) {
+                        tma_load_1d(sb, a.M + (size_t)slot0(m) * 32 * BB, (unsigned)wst * 32 * BB * 8, bars + st);
+                        tma_load_1d(sb + SM::kBlkBytes + SM::kDinvBytes, a.slot_col + (size_t)slot0(m) * 32,
+                                    (unsigned)wst * 128, bars + st);
+                    }
+                    if (NEED_DINV)
+                        tma_load_1d(sb + SM::kBlkBytes, a.dinv_s + (size_t)slice_id(t) * 32 * BB, SM::kDinvBytes, bars + st);
                 }
             }
         };
-        // speculative loads of the values that do not come from the ring
-        auto load_ext = [&](int t, const int (&cj)[kPrefetch], double (&ext)[kPrefetch][B]) {
-            if (t < ns) {
-                const SliceMeta m = metas[t % kMetaWin];
+        auto stage_cols = [&](int t) {
+            return reinterpret_cast<const int*>(stage0 + (size_t)(t % NS) * SM::kStageBytes + SM::kBlkBytes + SM::kDinvBytes);
+        };
+        // speculative loads for slice t (its stage must have landed): own input + external dependencies
+        auto load_ahead = [&](int t, int (&cj)[kPrefetch], double (&ext)[kPrefetch][B], double (&in)[B]) {
+            const SliceMeta m = metas[t % kMetaWin];
+            const int* cols = stage_cols(t);
+            const int q = m.q0 + lane;
 #pragma unroll
-                for (int s = 0; s < kPrefetch; ++s)
-                    if (cj[s] >= 0 && !in_ring(cj[s], m)) {
+            for (int s = 0; s < kPrefetch; ++s)
+                cj[s] = (lane < m.count && s < width(m)) ? cols[s * 32 + lane] : -1;
 #pragma unroll
-                        for (int r = 0; r < B; ++r)
-                            ext[s][r] = ld_relaxed(out + VIDX(a.n, cj[s], r));
-                    }
+            for (int s = 0; s < kPrefetch; ++s)
+                if (cj[s] >= 0 && !in_ring(cj[s], m))
+                    rec_load_strong<B>(out, (size_t)cj[s], ext[s]);
+            if (lane < m.count) {
+                if (UPPER) {
+                    rec_load_strong<B>(a.tmp, (size_t)q, in);
+                } else {
+                    const bool ghost = ILU0 && a.n_interior < a.n && a.r2n[q] >= a.n_interior;
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+                        in[r] = ghost ? (a.ghost_zero ? 0.0 : a.v[VIDX(a.n, q, r)]) : a.d[VIDX(a.n, q, r)];
+                }
             }
         };
 
-        int cjA[kPrefetch], cjB[kPrefetch], cjC[kPrefetch];
-        double extA[kPrefetch][B], extB[kPrefetch][B];
-        load_cols(0, cjA);
-        load_cols(1, cjB);
-        load_ext(0, cjA, extA);
-        // warm the L2 for the first slices
-        for (int t = lane; t < min(a.prefetch, ns); t += 32) {
-            const SliceMeta m = metas[t % kMetaWin];
-            if (width(m) > 0) {
-                l2_prefetch_bulk(a.M + (size_t)slot0(m) * 32 * BB, (unsigned)width(m) * 32 * BB * 8);
-                l2_prefetch_bulk(a.slot_col + (size_t)slot0(m) * 32, (unsigned)width(m) * 128);
-            }
+        for (int t = 0; t < NS - 1; ++t)
+            request(t);
+        int cjA[kPrefetch], cjB[kPrefetch];
+        double extA[kPrefetch][B], extB[kPrefetch][B], inA[B], inB[B];
+        bool haveA = false;
+        if (ns > 0) {
+            mbar_wait(bars + 0, 0);
+            load_ahead(0, cjA, extA, inA);
+            haveA = true;
         }
 
         for (int t = 0; t < ns; ++t) {
-            if (t > 0 && (t % (kMetaWin / 2)) == 0) { // refill the half window that has just been left
+            if (t > 0 && (t % (kMetaWin / 2)) == 0) {
                 __syncwarp();
                 fill_meta(t + kMetaWin / 2, kMetaWin / 2);
                 __syncwarp();
             }
+#ifdef OPMB200_PROFILE
+            long long tprev__ = clock64();
+#endif
+            const int st = t % NS;
+            const unsigned parity = (unsigned)(t / NS) & 1u;
             const SliceMeta m = metas[t % kMetaWin];
             const bool active = lane < m.count;
             const int q = m.q0 + lane;
             const int w = width(m);
             const int sr0 = slot0(m);
+            request(t + NS - 1); // its stage was released at the end of step t-1
+            PROF_MARK(0);
+            if (!haveA) {
+                mbar_wait(bars + st, parity);
+                load_ahead(t, cjA, extA, inA);
+            }
+            PROF_MARK(1);
+            const double* sblk = reinterpret_cast<const double*>(stage0 + (size_t)st * SM::kStageBytes);
+            const double* sdinv = reinterpret_cast<const double*>(stage0 + (size_t)st * SM::kStageBytes + SM::kBlkBytes);
 
-            // ---- demand loads of this slice (L2 hits thanks to the prefetch below) --------------------
-            double blk[kPrefetch][BB];
-#pragma unroll
-            for (int s = 0; s < kPrefetch; ++s)
-                if (cjA[s] >= 0) {
-#pragma unroll
-                    for (int e = 0; e < BB; ++e)
-                        blk[s][e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
+            // look ahead one slice if its stage has already landed (it was requested NS-1 steps ago)
+            bool haveB = (t + 1 < ns) && mbar_try_wait(bars + (t + 1) % NS, (unsigned)((t + 1) / NS) & 1u);
+            haveB = __all_sync(0xffffffffu, haveB);
+            if (haveB)
+                load_ahead(t + 1, cjB, extB, inB);
+            // far look-ahead: pull the stream of slice t+12 into the L2 (TMA covers the last hop only)
+            if (lane == 0 && t + 12 < ns) {
+                const SliceMeta mp = metas[(t + 12) % kMetaWin];
+                const int wp = min(width(mp), kPrefetch);
+                if (wp > 0) {
+                    l2_prefetch_bulk(a.M + (size_t)slot0(mp) * 32 * BB, (unsigned)wp * 32 * BB * 8);
+                    l2_prefetch_bulk(a.slot_col + (size_t)slot0(mp) * 32, (unsigned)wp * 128);
                 }
-            double di[BB], rhs[B], yi[B];
+                if (NEED_DINV)
+                    l2_prefetch_bulk(a.dinv_s + (size_t)slice_id(t + 12) * 32 * BB, SM::kDinvBytes);
+            }
+
+            PROF_MARK(2);
+            double rhs[B], yi[B], res[B];
             bool ghost = false;
             if (active) {
-                if (!(ILU0 && !UPPER)) {
-#pragma unroll
-                    for (int e = 0; e < BB; ++e)
-                        di[e] = __ldcs(a.dinv + (size_t)q * BB + e);
-                }
                 if (ILU0 && a.n_interior < a.n)
                     ghost = a.r2n[q] >= a.n_interior;
-                if (!UPPER) {
 #pragma unroll
-                    for (int r = 0; r < B; ++r)
-                        rhs[r] = ghost ? (a.ghost_zero ? 0.0 : a.v[VIDX(a.n, q, r)]) : a.d[VIDX(a.n, q, r)];
-#pragma unroll
-                    for (int r = 0; r < B; ++r)
-                        st_relaxed(a.v + VIDX(a.n, q, r), sentinel());
-                } else {
-#pragma unroll
-                    for (int r = 0; r < B; ++r) {
-                        yi[r] = a.tmp[VIDX(a.n, q, r)];
-                        rhs[r] = (ILU0) ? yi[r] : 0.0;
-                    }
+                for (int r = 0; r < B; ++r) {
+                    yi[r] = inA[r];
+                    rhs[r] = UPPER ? (ILU0 ? inA[r] : 0.0) : inA[r];
                 }
-            }
-            // ---- look ahead: columns of slice t+2, speculative dependency values of slice t+1 -----------
-            load_cols(t + 2, cjC);
-            load_ext(t + 1, cjB, extB);
-            if (lane == 0 && t + a.prefetch < ns) {
-                const SliceMeta mp = metas[(t + a.prefetch) % kMetaWin];
-                if (width(mp) > 0) {
-                    l2_prefetch_bulk(a.M + (size_t)slot0(mp) * 32 * BB, (unsigned)width(mp) * 32 * BB * 8);
-                    l2_prefetch_bulk(a.slot_col + (size_t)slot0(mp) * 32, (unsigned)width(mp) * 128);
-                }
-                if (!(ILU0 && !UPPER))
-                    l2_prefetch_bulk(a.dinv + (size_t)mp.q0 * BB, (unsigned)mp.count * BB * 8);
-                const double* in = UPPER ? a.tmp : a.d;
-#pragma unroll
-                for (int r = 0; r < B; ++r)
-                    l2_prefetch_bulk(in + VIDX(a.n, mp.q0, r), (unsigned)mp.count * 8);
-            }
+                if (!UPPER)
+                    rec_store_sentinel<B>(a.vpoll, (size_t)q); // arm the upper sweep's records
 
-            // ---- dependencies: ring (same chunk, recent) or L2 (other chunks) ---------------------------
-            if (active) {
+                // ---- dependencies: ring (same chunk, recent) or L2 (other chunks) -----------------------
                 double xv[kPrefetch][B];
                 unsigned pending = 0;
 #pragma unroll
@@ -1181,44 +1319,37 @@ __global__ void __launch_bounds__(kChunkWarps * 32, 2) chunk_sweep_kernel(ChunkS
                             for (int r = 0; r < B; ++r)
                                 xv[s][r] = ring[r * kRing + (cjA[s] & (kRing - 1))];
                         } else {
-                            bool ok = true;
 #pragma unroll
-                            for (int r = 0; r < B; ++r) {
+                            for (int r = 0; r < B; ++r)
                                 xv[s][r] = extA[s][r];
-                                ok = ok && !is_sentinel(xv[s][r]);
-                            }
-                            if (!ok)
+                            if (!rec_valid<B>(xv[s]) && !(a.debug & 1))
                                 pending |= 1u << s;
                         }
                     }
                 while (pending) {
 #pragma unroll
                     for (int s = 0; s < kPrefetch; ++s)
-                        if (pending & (1u << s)) {
-#pragma unroll
-                            for (int r = 0; r < B; ++r)
-                                xv[s][r] = ld_relaxed(out + VIDX(a.n, cjA[s], r));
-                        }
+                        if (pending & (1u << s))
+                            rec_load_strong<B>(out, (size_t)cjA[s], xv[s]);
 #pragma unroll
                     for (int s = 0; s < kPrefetch; ++s)
-                        if (pending & (1u << s)) {
-                            bool ok = true;
-#pragma unroll
-                            for (int r = 0; r < B; ++r)
-                                ok = ok && !is_sentinel(xv[s][r]);
-                            if (ok)
-                                pending &= ~(1u << s);
-                        }
+                        if ((pending & (1u << s)) && rec_valid<B>(xv[s]))
+                            pending &= ~(1u << s);
                 }
+                PROF_MARK(3);
 #pragma unroll
                 for (int s = 0; s < kPrefetch; ++s)
                     if (cjA[s] >= 0) {
+                        double blk[BB];
+#pragma unroll
+                        for (int e = 0; e < BB; ++e)
+                            blk[e] = sblk[(s * BB + e) * 32 + lane];
                         if (UPPER && !ILU0)
-                            blk_umv<B>(blk[s], xv[s], rhs);
+                            blk_umv<B>(blk, xv[s], rhs);
                         else
-                            blk_mmv<B>(blk[s], xv[s], rhs);
+                            blk_mmv<B>(blk, xv[s], rhs);
                     }
-                for (int s = kPrefetch; s < w; ++s) { // rows wider than the register window
+                for (int s = kPrefetch; s < w; ++s) { // rows wider than the staged window: straight from memory
                     const int cc = __ldg(a.slot_col + (size_t)(sr0 + s) * 32 + lane);
                     if (cc < 0)
                         continue;
@@ -1231,25 +1362,23 @@ __global__ void __launch_bounds__(kChunkWarps * 32, 2) chunk_sweep_kernel(ChunkS
                         for (int r = 0; r < B; ++r)
                             xs[r] = ring[r * kRing + (cc & (kRing - 1))];
                     } else {
-                        bool ok;
                         do {
-                            ok = true;
-#pragma unroll
-                            for (int r = 0; r < B; ++r) {
-                                xs[r] = ld_relaxed(out + VIDX(a.n, cc, r));
-                                ok = ok && !is_sentinel(xs[r]);
-                            }
-                        } while (!ok);
+                            rec_load_strong<B>(out, (size_t)cc, xs);
+                        } while (!rec_valid<B>(xs) && !(a.debug & 1));
                     }
                     if (UPPER && !ILU0)
                         blk_umv<B>(bl, xs, rhs);
                     else
                         blk_mmv<B>(bl, xs, rhs);
                 }
-            }
-            // ---- finish the rows, publish to the ring and to memory -------------------------------------
-            double res[B];
-            if (active) {
+
+                // ---- finish the rows --------------------------------------------------------------------------
+                double di[BB];
+                if (NEED_DINV) {
+#pragma unroll
+                    for (int e = 0; e < BB; ++e)
+                        di[e] = sdinv[e * 32 + lane];
+                }
                 if (!UPPER) {
                     if (ILU0) {
 #pragma unroll
@@ -1276,24 +1405,34 @@ __global__ void __launch_bounds__(kChunkWarps * 32, 2) chunk_sweep_kernel(ChunkS
                 for (int r = 0; r < B; ++r)
                     res[r] = guard(res[r]);
             }
-            __syncwarp(); // every lane has finished reading the ring
+            PROF_MARK(4);
+            __syncwarp(); // every lane has finished reading the ring and this stage
+            PROF_MARK(5);
             if (active) {
 #pragma unroll
                 for (int r = 0; r < B; ++r) {
                     ring[r * kRing + (q & (kRing - 1))] = res[r];
-                    st_relaxed(out + VIDX(a.n, q, r), res[r]);
                     if (UPPER)
-                        a.tmp[VIDX(a.n, q, r)] = sentinel();
+                        a.v[VIDX(a.n, q, r)] = res[r];
                 }
+                rec_store_strong<B>(out, (size_t)q, res);
+                if (UPPER)
+                    rec_store_sentinel<B>(a.tmp, (size_t)q);
             }
             __syncwarp(); // ring writes visible to the whole warp before the next slice
+            PROF_MARK(6);
+            haveA = haveB;
+            if (haveB) {
 #pragma unroll
-            for (int s = 0; s < kPrefetch; ++s) {
-                cjA[s] = cjB[s];
-                cjB[s] = cjC[s];
+                for (int s = 0; s < kPrefetch; ++s) {
+                    cjA[s] = cjB[s];
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+                        extA[s][r] = extB[s][r];
+                }
 #pragma unroll
                 for (int r = 0; r < B; ++r)
-                    extA[s][r] = extB[s][r];
+                    inA[r] = inB[r];
             }
         }
     }

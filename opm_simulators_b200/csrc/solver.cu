@@ -121,7 +121,7 @@ struct opmb200_solver {
     int schedule = 0;   // 0 levels, 1 chunks
     int chunk_rows = 0; // <= 0: automatic
     int prefetch = 12;  // L2 prefetch distance of the chunk sweeps, in slices
-    int debug_lower_only = 0;
+    int debug = 0;      // timing experiments (results are wrong when != 0)
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -131,8 +131,9 @@ struct opmb200_solver {
 
     DevBuf<SliceMeta> slices;
     DevBuf<int> slot_col, slot_src, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag, chunk_slice0;
-    DevBuf<double> A, F, dinv, vals_native;
-    DevBuf<double> vx, vr, vp, vv, vt, vy, vrt, vtmp, vw, nat0, nat1;
+    DevBuf<double> A, F, dinv, dinv_s, vals_native;
+    DevBuf<double> vx, vr, vp, vv, vt, vy, vrt, vw, nat0, nat1;
+    DevBuf<double> vtmp, vpoll; // dependency records of the sweeps, [n][2 or 4]
     DevBuf<double> partials, hist, sums, dot_out;
     DevBuf<unsigned int> counters; // [0] reduce arrivals, [1] ticket next, [2] ticket done
     DevBuf<Scalars> sc;
@@ -301,6 +302,7 @@ SweepArgs sweep_args(opmb200_solver* s, const double* d, double* v, int ghost_ze
     a.dinv = s->dinv.p;
     a.d = d;
     a.tmp = s->vtmp.p;
+    a.vpoll = s->vpoll.p;
     a.v = v;
     a.level_q0 = s->level_q0.p;
     a.n_levels = s->L.n_levels;
@@ -325,26 +327,28 @@ int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
         c.slices = a.slices;
         c.slot_col = a.slot_col;
         c.M = a.M;
-        c.dinv = a.dinv;
+        c.dinv_s = s->dinv_s.p;
         c.d = a.d;
         c.tmp = a.tmp;
+        c.vpoll = a.vpoll;
         c.v = a.v;
         c.r2n = a.r2n;
         c.n = a.n;
         c.n_interior = a.n_interior;
         c.ghost_zero = a.ghost_zero;
-        c.prefetch = s->prefetch;
+        c.debug = s->debug;
         c.ticket = a.ticket;
         c.sc = a.sc;
         c.check_done = a.check_done;
         const int cgrid = std::max(1, (s->L.n_chunks + kChunkWarps - 1) / kChunkWarps);
         DISPATCH_B(s->b, {
+            constexpr int smem = ChunkSmem<B>::kCtaBytes;
             if (s->prec == PREC_ILU0) {
-                if (upper) chunk_sweep_kernel<B, true, true><<<cgrid, kChunkWarps * 32, 0, s->stream>>>(c);
-                else chunk_sweep_kernel<B, true, false><<<cgrid, kChunkWarps * 32, 0, s->stream>>>(c);
+                if (upper) chunk_sweep_kernel<B, true, true><<<cgrid, kChunkWarps * 32, smem, s->stream>>>(c);
+                else chunk_sweep_kernel<B, true, false><<<cgrid, kChunkWarps * 32, smem, s->stream>>>(c);
             } else {
-                if (upper) chunk_sweep_kernel<B, false, true><<<cgrid, kChunkWarps * 32, 0, s->stream>>>(c);
-                else chunk_sweep_kernel<B, false, false><<<cgrid, kChunkWarps * 32, 0, s->stream>>>(c);
+                if (upper) chunk_sweep_kernel<B, false, true><<<cgrid, kChunkWarps * 32, smem, s->stream>>>(c);
+                else chunk_sweep_kernel<B, false, false><<<cgrid, kChunkWarps * 32, smem, s->stream>>>(c);
             }
         });
         return check_launch(s, upper ? "upper chunk sweep" : "lower chunk sweep");
@@ -371,11 +375,6 @@ int prec_apply(opmb200_solver* s, const double* d, double* v, int ghost_zero, in
     }
     const SweepArgs a = sweep_args(s, d, v, ghost_zero, check_done);
     TRY(launch_sweep(s, a, false));
-    if (s->debug_lower_only) { // test hook: expose the intermediate y of the lower sweep
-        CUDA_TRY(cudaMemcpyAsync(v, s->vtmp.p, s->len() * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
-        fill_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->vtmp.p, s->len(), sentinel_host());
-        return check_launch(s, "fill");
-    }
     TRY(launch_sweep(s, a, true));
     TRY(copy_owner_to_all(s, v));
     if (s->prec == PREC_ILU0 && std::abs(s->relaxation - 1.0) > 1e-15) {
@@ -401,6 +400,7 @@ int prec_update(opmb200_solver* s)
     a.trip_src = s->trip_src.p;
     a.trip_dst = s->trip_dst.p;
     a.dinv = s->dinv.p;
+    a.dinv_s = s->dinv_s.p;
     a.row_flag = s->row_flag.p;
     a.epoch = s->epoch;
     a.ticket = s->ticket();
@@ -491,7 +491,7 @@ int parse_options(opmb200_solver* s, const char* json)
         s->schedule = sched == "chunks" ? 1 : 0;
         s->chunk_rows = prm.get<int>("b200.chunk_rows", 0);
         s->prefetch = std::max(1, std::min(24, prm.get<int>("b200.prefetch_slices", 12)));
-        s->debug_lower_only = prm.get<int>("b200.debug_lower_only", 0);
+        s->debug = prm.get<int>("b200.debug_timing", 0);
     } catch (const std::exception& e) {
         return fail(OPMB200_BAD_OPTIONS, e.what());
     }
@@ -795,11 +795,13 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
     }
     CUDA_TRY(s->A.alloc((size_t)L.n_slot_rows * kSlice * BB));
     CUDA_TRY(s->dinv.alloc((size_t)L.n * BB));
+    CUDA_TRY(s->dinv_s.alloc((size_t)std::max(L.n_slices, 1) * kSlice * BB));
+    CUDA_TRY(cudaMemsetAsync(s->dinv_s.p, 0, s->dinv_s.n * sizeof(double), st));
     CUDA_TRY(s->row_flag.alloc((size_t)L.n));
     CUDA_TRY(cudaMemsetAsync(s->row_flag.p, 0, std::max<size_t>(L.n, 1) * sizeof(int), st));
     CUDA_TRY(s->vals_native.alloc((size_t)nnzb * BB));
     const size_t len = (size_t)L.n * block_size;
-    for (DevBuf<double>* v : {&s->vx, &s->vr, &s->vp, &s->vv, &s->vt, &s->vy, &s->vrt, &s->vtmp, &s->vw, &s->nat0, &s->nat1}) {
+    for (DevBuf<double>* v : {&s->vx, &s->vr, &s->vp, &s->vv, &s->vt, &s->vy, &s->vrt, &s->vw, &s->nat0, &s->nat1}) {
         CUDA_TRY(v->alloc(len));
         CUDA_TRY(cudaMemsetAsync(v->p, 0, std::max<size_t>(len, 1) * sizeof(double), st));
     }
@@ -813,9 +815,13 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
     CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, 4 * sizeof(unsigned int), st));
     CUDA_TRY(s->sc.alloc(1));
     CUDA_TRY(cudaMemsetAsync(s->sc.p, 0, sizeof(Scalars), st));
-    // the sweeps' intermediate vector is all-sentinel between applies
-    fill_kernel<<<s->vec_grid, 256, 0, st>>>(s->vtmp.p, (int64_t)len, sentinel_host());
-    TRY(check_launch(s.get(), "fill"));
+    // the sweeps' dependency records are all-sentinel between applies
+    const size_t rec_len = (size_t)L.n * (block_size <= 2 ? 2 : 4);
+    for (DevBuf<double>* v : {&s->vtmp, &s->vpoll}) {
+        CUDA_TRY(v->alloc(rec_len));
+        fill_kernel<<<s->vec_grid, 256, 0, st>>>(v->p, (int64_t)rec_len, sentinel_host());
+        TRY(check_launch(s.get(), "fill"));
+    }
 
     // ---- halo lists -> positions --------------------------------------------------------------------
     if (s->n_ranks > 1) {
@@ -840,6 +846,15 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
         CUDA_TRY(s->recv_rows.upload(rp, st));
         CUDA_TRY(s->send_buf.alloc(sp.size() * block_size));
         CUDA_TRY(s->recv_buf.alloc(rp.size() * block_size));
+    }
+    if (s->schedule == 1) {
+        DISPATCH_B(block_size, {
+            constexpr int smem = ChunkSmem<B>::kCtaBytes;
+            CUDA_TRY(cudaFuncSetAttribute(chunk_sweep_kernel<B, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CUDA_TRY(cudaFuncSetAttribute(chunk_sweep_kernel<B, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CUDA_TRY(cudaFuncSetAttribute(chunk_sweep_kernel<B, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CUDA_TRY(cudaFuncSetAttribute(chunk_sweep_kernel<B, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        });
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     *out = s.release();
@@ -1152,6 +1167,19 @@ int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, doubl
         *algorithmic_bytes = bytes;
     return OPMB200_SUCCESS;
 }
+
+#ifdef OPMB200_PROFILE
+int opmb200_prof_read(unsigned long long* out16, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(g_prof, z, sizeof z);
+    }
+    return 0;
+}
+#endif
 
 int opmb200_timer_start(opmb200_solver* s)
 {
