@@ -20,6 +20,7 @@ namespace opmb200 {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kCtaThreads = kWarpsPerCta * 32;
+constexpr int kPrefetch = 3; // block slots a lane holds in registers / stages before a dependency wait
 constexpr unsigned long long kSentinelBits = 0xFFF8B200DEADC0DEull; // quiet NaN never produced by arithmetic
 
 struct SliceMeta { // 32 bytes
@@ -719,6 +720,7 @@ struct FactorArgs {
     const int* trip_dst;
     double* dinv;           // [n][b*b] by position
     double* dinv_s;         // the same in slice layout [slice][b*b][32] (what the chunk sweeps stage)
+    double* dinv_rec;       // DILU factorisation: Dinv as dependency records [n][b][Rec<b>::W]
     int* row_flag;          // [n]
     int epoch;
     Ticket ticket;
@@ -733,6 +735,9 @@ __device__ __forceinline__ void wait_row(const int* flag, int epoch)
     __threadfence();
 }
 
+// Dinv_j travels from row to row as B dependency records (one per block row, see Rec<B>) in
+// `dinv_rec`, armed with sentinels by fill_kernel before the launch: a consumer samples a finished
+// Dinv_j with B strong vector loads, no flag and no fence on the producer side.
 template <int B>
 __global__ void __launch_bounds__(kCtaThreads) dilu_factor_kernel(FactorArgs a)
 {
@@ -748,38 +753,85 @@ __global__ void __launch_bounds__(kCtaThreads) dilu_factor_kernel(FactorArgs a)
 #pragma unroll
             for (int e = 0; e < BB; ++e)
                 D[e] = a.A[elem_index<BB>(m.base + m.wl, lane, e)];
-            for (int s = 0; s < m.wl; ++s) {
-                const int c = a.slot_col[(size_t)(m.base + s) * 32 + lane];
-                if (c < 0)
-                    continue;
-                const int tr = a.l_transpose[(size_t)(m.lrank + s) * 32 + lane];
-                if (tr < 0)
-                    continue; // A_ji not stored: no contribution (DILU.hpp:196-201)
-                double Aij[BB], Aji[BB], Dj[BB], T1[BB], T2[BB];
+            for (int s0 = 0; s0 < m.wl; s0 += kPrefetch) {
+                // everything that does not depend on other rows first ...
+                int cj[kPrefetch];
+                double Aij[kPrefetch][BB], Aji[kPrefetch][BB];
 #pragma unroll
-                for (int e = 0; e < BB; ++e) {
-                    Aij[e] = a.A[elem_index<BB>(m.base + s, lane, e)];
-                    Aji[e] = a.A[elem_index_slot<BB>(tr, e)];
+                for (int k = 0; k < kPrefetch; ++k) {
+                    const int s = s0 + k;
+                    cj[k] = -1;
+                    if (s < m.wl) {
+                        const int c = a.slot_col[(size_t)(m.base + s) * 32 + lane];
+                        const int tr = c >= 0 ? a.l_transpose[(size_t)(m.lrank + s) * 32 + lane] : -1;
+                        if (tr >= 0) { // A_ji stored: the term exists (DILU.hpp:196-201)
+                            cj[k] = c;
+#pragma unroll
+                            for (int e = 0; e < BB; ++e) {
+                                Aij[k][e] = a.A[elem_index<BB>(m.base + s, lane, e)];
+                                Aji[k][e] = a.A[elem_index_slot<BB>(tr, e)];
+                            }
+                        }
+                    }
                 }
-                wait_row<BB>(a.row_flag + c, a.epoch);
+                // ... then wait for the Dinv_j, all outstanding ones per round trip
+                double Dj[kPrefetch][BB];
+                unsigned pending = 0;
 #pragma unroll
-                for (int e = 0; e < BB; ++e)
-                    Dj[e] = ld_relaxed(a.dinv + (size_t)c * BB + e);
-                blk_mm<B>(Aij, Dj, T1);
-                blk_mm<B>(T1, Aji, T2);
+                for (int k = 0; k < kPrefetch; ++k)
+                    if (cj[k] >= 0)
+                        pending |= 1u << k;
+                while (pending) {
 #pragma unroll
-                for (int e = 0; e < BB; ++e)
-                    D[e] -= T2[e];
+                    for (int k = 0; k < kPrefetch; ++k)
+                        if (pending & (1u << k)) {
+#pragma unroll
+                            for (int r = 0; r < B; ++r) {
+                                double row[B];
+                                rec_load_strong<B>(a.dinv_rec, (size_t)cj[k] * B + r, row);
+#pragma unroll
+                                for (int c2 = 0; c2 < B; ++c2)
+                                    Dj[k][r * B + c2] = row[c2];
+                            }
+                        }
+#pragma unroll
+                    for (int k = 0; k < kPrefetch; ++k)
+                        if (pending & (1u << k)) {
+                            bool ok = true;
+#pragma unroll
+                            for (int e = 0; e < BB; ++e)
+                                ok = ok && !is_sentinel(Dj[k][e]);
+                            if (ok)
+                                pending &= ~(1u << k);
+                        }
+                }
+#pragma unroll
+                for (int k = 0; k < kPrefetch; ++k)
+                    if (cj[k] >= 0) { // Dinv_temp -= (A_ij Dinv_j) A_ji, slots in ascending column order
+                        double T1[BB], T2[BB];
+                        blk_mm<B>(Aij[k], Dj[k], T1);
+                        blk_mm<B>(T1, Aji[k], T2);
+#pragma unroll
+                        for (int e = 0; e < BB; ++e)
+                            D[e] -= T2[e];
+                    }
             }
             if (!blk_invert<B>(D))
                 a.sc->factor_error = 1;
 #pragma unroll
             for (int e = 0; e < BB; ++e) {
-                st_relaxed(a.dinv + (size_t)q * BB + e, D[e]);
+                D[e] = guard(D[e]);
+                a.dinv[(size_t)q * BB + e] = D[e];
                 a.dinv_s[((size_t)S * BB + e) * 32 + lane] = D[e];
             }
-            __threadfence();
-            st_relaxed(a.row_flag + q, a.epoch);
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                double row[B];
+#pragma unroll
+                for (int c2 = 0; c2 < B; ++c2)
+                    row[c2] = D[r * B + c2];
+                rec_store_strong<B>(a.dinv_rec, (size_t)q * B + r, row);
+            }
         }
     }
     return_ticket(a.ticket);
@@ -881,7 +933,6 @@ struct SweepArgs {
     int check_done;
 };
 
-constexpr int kPrefetch = 3; // block slots held in registers before the dependency wait
 
 template <int B, bool ILU0, bool UPPER>
 __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(SweepArgs a)

@@ -131,7 +131,7 @@ struct opmb200_solver {
 
     DevBuf<SliceMeta> slices;
     DevBuf<int> slot_col, slot_src, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag, chunk_slice0;
-    DevBuf<double> A, F, dinv, dinv_s, vals_native;
+    DevBuf<double> A, F, dinv, dinv_s, dinv_rec, vals_native;
     DevBuf<double> vx, vr, vp, vv, vt, vy, vrt, vw, nat0, nat1;
     DevBuf<double> vtmp, vpoll; // dependency records of the sweeps, [n][2 or 4]
     DevBuf<double> partials, hist, sums, dot_out;
@@ -401,11 +401,16 @@ int prec_update(opmb200_solver* s)
     a.trip_dst = s->trip_dst.p;
     a.dinv = s->dinv.p;
     a.dinv_s = s->dinv_s.p;
+    a.dinv_rec = s->dinv_rec.p;
     a.row_flag = s->row_flag.p;
     a.epoch = s->epoch;
     a.ticket = s->ticket();
     a.sc = s->sc.p;
     const int grid = s->slice_grid();
+    if (s->prec == PREC_DILU) { // arm the Dinv dependency records
+        fill_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->dinv_rec.p, (int64_t)s->dinv_rec.n, sentinel_host());
+        TRY(check_launch(s, "fill"));
+    }
     DISPATCH_B(s->b, {
         if (s->prec == PREC_ILU0) ilu0_factor_kernel<B><<<grid, kCtaThreads, 0, s->stream>>>(a);
         else dilu_factor_kernel<B><<<grid, kCtaThreads, 0, s->stream>>>(a);
@@ -795,6 +800,8 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
     }
     CUDA_TRY(s->A.alloc((size_t)L.n_slot_rows * kSlice * BB));
     CUDA_TRY(s->dinv.alloc((size_t)L.n * BB));
+    if (s->prec == PREC_DILU)
+        CUDA_TRY(s->dinv_rec.alloc((size_t)L.n * block_size * (block_size <= 2 ? 2 : 4)));
     CUDA_TRY(s->dinv_s.alloc((size_t)std::max(L.n_slices, 1) * kSlice * BB));
     CUDA_TRY(cudaMemsetAsync(s->dinv_s.p, 0, s->dinv_s.n * sizeof(double), st));
     CUDA_TRY(s->row_flag.alloc((size_t)L.n));
