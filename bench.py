@@ -149,6 +149,12 @@ def run_b200(args):
     opts = {"solver": "bicgstab", "tol": args.tol, "maxiter": 200, "verbosity": 0,
             "preconditioner": {"type": args.prec, "relaxation": 1.0}}
     fs = FlexibleSolver(MatrixAdapter(A, w["n_interior"], comm, w["halo"]), opts)
+    if world > 1 and args.collectives == "p2p":
+        def allgather(blob):
+            out = [None] * world
+            dist.all_gather_object(out, blob)
+            return out
+        fs.enable_p2p(allgather)
     info0 = fs.info()
 
     # ---- device-resident arm ---------------------------------------------------------------------
@@ -247,7 +253,7 @@ def run_b200(args):
                                    f"step = value refresh + refactorisation + solve",
                        "rhs": "N(0,1)", "cells_per_gpu": int(w["n_interior"]), "levels": info0["n_levels"],
                        "l2": "inputs larger than L2 (matrix 560 MB per GPU), no explicit flush",
-                       "partition": "z-slabs, block-Jacobi DILU, NCCL halo + all-reduce" if world > 1 else "serial"},
+                       "partition": (f"z-slabs, block-Jacobi DILU, halo + all-reduce over {args.collectives}") if world > 1 else "serial"},
             "iterations_per_solve": iters / args.steps, "iters_per_s": round(iters / (ms_dev * 1e-3), 2),
             "time_to_solve_ms": round(ms_dev / args.steps, 4), "wall_ms_per_step": round(wall * 1e3 / args.steps, 4),
             "update_ms": round(float(np.mean(t_upd)), 4), "solve_ms": round(float(np.mean(t_slv)), 4),
@@ -362,6 +368,8 @@ def main():
     ap.add_argument("--prec", default="dilu", choices=["dilu", "ilu0"])
     ap.add_argument("--tol", type=float, default=1e-2)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--collectives", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1: collectives inside the library's kernels over NVLink peer memory, or NCCL calls")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

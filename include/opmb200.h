@@ -194,6 +194,19 @@ int opmb200_get_history(opmb200_solver* s, double* hist, int capacity, int* coun
 int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, double* ms_per_launch,
                         double* algorithmic_bytes);
 
+/* ---- peer-to-peer collectives (optional, multi-GPU) -------------------------------------------
+ * Replaces the NCCL calls of the Krylov loop by collectives that run INSIDE the library's own
+ * kernels over NVLink peer memory (one process per GPU, peers mapped with CUDA IPC): the last CTA
+ * of every fused reduction kernel pushes its partial sums into the peers' mailboxes and adds the
+ * partials of all ranks in rank order (= OwnerOverlapCopyCommunication::sum, gpuistl/GpuSender.hpp:
+ * 89-95), and the halo copy writes owner rows straight into the neighbour's receive buffer
+ * (= copyOwnerToAll, gpuistl/GpuAwareMPISender.hpp:55-136).
+ * Every rank exports one blob, the host all-gathers them in rank order (MPI_Allgather in Flow,
+ * torch.distributed in bench.py) and hands the concatenation to opmb200_p2p_import. */
+#define OPMB200_P2P_BLOB_BYTES 1024
+int opmb200_p2p_export(opmb200_solver* s, void* blob);
+int opmb200_p2p_import(opmb200_solver* s, const void* blobs_in_rank_order);
+
 /* Device-time stopwatch on the handle's own stream (CUDA events): start, run any sequence of
  * calls on the handle, stop -> elapsed milliseconds between the two events. */
 int opmb200_timer_start(opmb200_solver* s);

@@ -77,6 +77,8 @@ PROTOTYPES = {
     "opmb200_get_ilu0": (C.c_int, [_vp, _vp]),
     "opmb200_get_history": (C.c_int, [_vp, _vp, C.c_int, C.POINTER(C.c_int)]),
     "opmb200_time_kernel": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "opmb200_p2p_export": (C.c_int, [_vp, _vp]),
+    "opmb200_p2p_import": (C.c_int, [_vp, _vp]),
     "opmb200_timer_start": (C.c_int, [_vp]),
     "opmb200_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
 }

@@ -391,13 +391,92 @@ __device__ __forceinline__ void cta_sum(double (&v)[ND], double* smem /* [ND][32
     }
 }
 
+// ---- peer-to-peer collectives over NVLink (one process per GPU, peers' arenas mapped with CUDA IPC) ----
+constexpr int kMaxRanks = 16;
+constexpr int kMaxNeighbors = 16;
+struct P2PDev {
+    int rank, size;
+    double* mbox[kMaxRanks]; // rank p's mailboxes: records [2 parities][size senders][4 doubles]
+};
+
 struct ReduceCtx {
     double* partials;      // [ND][max grid]
     unsigned int* counter; // self-resetting arrival counter
     int stride;            // max grid
-    double* sums;          // multi-rank: the local sums land here, an NCCL all-reduce and
+    double* sums;          // multi-rank over NCCL: the local sums land here, ncclAllReduce and
     int defer;             //   epilogue_kernel follow on the stream (defer != 0)
+    const P2PDev* p2p;     // multi-rank over peer memory: the all-reduce happens inside this kernel
+    unsigned long long seq; //   sequence number of this reduction (same on every rank)
 };
+
+__device__ __forceinline__ void st_sys(double* p, double v)
+{
+    asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_sys(unsigned long long* p, unsigned long long v)
+{
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_sys(int* p, int v)
+{
+    asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ double ld_sys(const double* p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_sys(const unsigned long long* p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_sys(const int* p)
+{
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All-reduce (sum) of ND <= 2 doubles across the ranks, executed by warp 0 of ONE CTA per rank:
+// lane p pushes this rank's partial into rank p's mailbox over NVLink (values, system fence, then
+// the sequence number as the flag), then waits for rank p's partial in its own mailbox.  The
+// partials are added in rank order on every rank, so all ranks obtain bitwise identical sums.
+// Mailboxes are double-buffered on the parity of the sequence number: a rank can be at most one
+// reduction ahead of the slowest rank, because it needs everybody's partial to finish one.
+template <int ND>
+__device__ __forceinline__ void p2p_allreduce(const P2PDev& c, unsigned long long seq, double (&acc)[ND])
+{
+    const int lane = threadIdx.x & 31;
+    const int par = (int)(seq & 1ull);
+    double v[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+        v[d] = 0.0;
+    if (lane < c.size) {
+        double* dst = c.mbox[lane] + (size_t)(par * c.size + c.rank) * 4;
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            st_sys(dst + d, acc[d]);
+        __threadfence_system();
+        st_sys(reinterpret_cast<unsigned long long*>(dst + 3), seq);
+        const double* src = c.mbox[c.rank] + (size_t)(par * c.size + lane) * 4;
+        while (ld_sys(reinterpret_cast<const unsigned long long*>(src + 3)) != seq) {}
+        __threadfence_system();
+#pragma unroll
+        for (int d = 0; d < ND; ++d)
+            v[d] = ld_sys(src + d);
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) {
+        double s = 0.0;
+        for (int p = 0; p < c.size; ++p)
+            s += __shfl_sync(0xffffffffu, v[d], p);
+        acc[d] = s;
+    }
+}
 
 __device__ void run_epilogue(int epi, Scalars* sc, double* hist, const double* s, double* dot_out)
 {
@@ -511,6 +590,8 @@ __device__ __forceinline__ void grid_reduce(double (&v)[ND], const ReduceCtx& rc
     }
     __syncthreads();
     cta_sum<ND>(acc, red_smem);
+    if (rc.p2p && threadIdx.x < 32)
+        p2p_allreduce<ND>(*rc.p2p, rc.seq, acc);
     if (threadIdx.x == 0) {
         *rc.counter = 0u;
         if (rc.defer) {
@@ -1605,6 +1686,76 @@ __global__ void scatter_rows_kernel(int64_t n, int cnt, const int* __restrict__ 
 {
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < cnt * B; t += gridDim.x * blockDim.x)
         v[VIDX(n, rows[t / B], t % B)] = buf[t];
+}
+
+// ---- halo exchange over peer memory: copyOwnerToAll without NCCL --------------------------------------
+struct HaloDev {
+    int nn;                          // neighbours
+    int epoch;                       // exchange number (host counter, same on every rank)
+    int send_ptr[kMaxNeighbors + 1]; // rows sent to neighbour k: send_rows[send_ptr[k] .. send_ptr[k+1])
+    int recv_ptr[kMaxNeighbors + 1];
+    double* peer_recv[kMaxNeighbors]; // where neighbour k expects my rows (in ITS arena)
+    int* peer_dflag[kMaxNeighbors];   // "your data has landed" flag in neighbour k's arena
+    int* peer_ack[kMaxNeighbors];     // "I have consumed your data" flag in neighbour k's arena
+    const double* my_recv;            // my receive buffer (neighbours write into it)
+    int* my_dflag;                    // [nn] set by the neighbours
+    int* my_ack;                      // [nn] set by the neighbours
+};
+
+// pack the owner rows a neighbour holds as copies straight into the neighbour's receive buffer
+template <int B>
+__global__ void __launch_bounds__(256) halo_push_kernel(HaloDev h, int64_t n, const int* __restrict__ send_rows,
+                                                        const double* __restrict__ v, unsigned int* counter)
+{
+    // flow control: the neighbour must have consumed the previous exchange before we overwrite it
+    if ((int)threadIdx.x < h.nn)
+        while (ld_sys(h.my_ack + threadIdx.x) < h.epoch - 1) {}
+    __syncthreads();
+    const int total = h.send_ptr[h.nn] * B;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int row = t / B, c = t - row * B;
+        int k = 0;
+        while (row >= h.send_ptr[k + 1])
+            ++k;
+        h.peer_recv[k][(size_t)(row - h.send_ptr[k]) * B + c] = v[VIDX(n, send_rows[row], c)];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) {
+            *counter = 0u;
+            __threadfence_system();
+            for (int k = 0; k < h.nn; ++k)
+                st_sys(h.peer_dflag[k], h.epoch);
+        }
+    }
+}
+
+// wait for every neighbour's rows, scatter them into the ghost rows, acknowledge
+template <int B>
+__global__ void __launch_bounds__(256) halo_pull_kernel(HaloDev h, int64_t n, const int* __restrict__ recv_rows, double* __restrict__ v,
+                                                        unsigned int* counter)
+{
+    if ((int)threadIdx.x < h.nn)
+        while (ld_sys(h.my_dflag + threadIdx.x) != h.epoch) {}
+    __threadfence_system();
+    __syncthreads();
+    const int total = h.recv_ptr[h.nn] * B;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+        const int row = t / B, c = t - row * B;
+        v[VIDX(n, recv_rows[row], c)] = __ldcg(h.my_recv + t); // written by a peer: read at the L2
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned int done = atomicAdd(counter, 1u);
+        if (done == gridDim.x - 1) {
+            *counter = 0u;
+            for (int k = 0; k < h.nn; ++k)
+                st_sys(h.peer_ack[k], h.epoch);
+        }
+    }
 }
 
 } // namespace opmb200

@@ -146,6 +146,15 @@ struct opmb200_solver {
     std::vector<int> nb_rank, send_ptr, recv_ptr;
     DevBuf<int> send_rows, recv_rows; // positions
     DevBuf<double> send_buf, recv_buf;
+    // peer-to-peer mode (opmb200_p2p_export / _import): collectives run inside our own kernels
+    bool p2p = false;
+    DevBuf<unsigned char> arena; // mailboxes + halo receive buffer + flags, mapped by the peers through CUDA IPC
+    size_t off_mbox = 0, off_recv = 0, off_dflag = 0, off_ack = 0;
+    DevBuf<P2PDev> p2p_dev;
+    HaloDev halo_dev {};
+    std::vector<void*> peer_base; // IPC mappings to close
+    unsigned long long seq = 0;   // reduction sequence number
+    int halo_epoch = 0;
 
     double t_analysis_s = 0, t_update_ms = 0, t_solve_ms = 0;
     int64_t launches = 0;
@@ -157,6 +166,9 @@ struct opmb200_solver {
             cudaFreeHost(h_sc);
         if (h_small)
             cudaFreeHost(h_small);
+        for (void* pb : peer_base)
+            if (pb)
+                cudaIpcCloseMemHandle(pb);
         for (cudaEvent_t e : {ev0, ev1, ev_iter[0], ev_iter[1], ev_t0, ev_t1})
             if (e)
                 cudaEventDestroy(e);
@@ -165,7 +177,13 @@ struct opmb200_solver {
     }
 
     int64_t len() const { return L.n * b; }
-    ReduceCtx rctx() { return ReduceCtx {partials.p, counters.p, max_grid, sums.p, n_ranks > 1 ? 1 : 0}; }
+    // one call per reduction kernel launch: in p2p mode every call consumes a sequence number
+    ReduceCtx rctx()
+    {
+        if (p2p)
+            return ReduceCtx {partials.p, counters.p, max_grid, sums.p, 0, p2p_dev.p, ++seq};
+        return ReduceCtx {partials.p, counters.p, max_grid, sums.p, n_ranks > 1 ? 1 : 0, nullptr, 0ull};
+    }
     Ticket ticket() { return Ticket {counters.p + 1, counters.p + 2}; }
     int slice_grid() const { return std::max(1, (L.n_slices + kWarpsPerCta - 1) / kWarpsPerCta); }
 };
@@ -197,6 +215,17 @@ int copy_owner_to_all(opmb200_solver* s, double* v)
         return OPMB200_SUCCESS;
     const int b = s->b;
     const int ns = s->send_ptr.back(), nr = s->recv_ptr.back();
+    if (s->p2p) {
+        // peer memory: push my owner rows into the neighbours' receive buffers, then pull theirs
+        HaloDev h = s->halo_dev;
+        h.epoch = ++s->halo_epoch;
+        const int gpush = std::max(1, std::min(64, (ns * b + 255) / 256));
+        const int gpull = std::max(1, std::min(64, (nr * b + 255) / 256));
+        DISPATCH_B(b, (halo_push_kernel<B><<<gpush, 256, 0, s->stream>>>(h, s->L.n, s->send_rows.p, v, s->counters.p + 3)));
+        TRY(check_launch(s, "halo_push"));
+        DISPATCH_B(b, (halo_pull_kernel<B><<<gpull, 256, 0, s->stream>>>(h, s->L.n, s->recv_rows.p, v, s->counters.p + 3)));
+        return check_launch(s, "halo_pull");
+    }
     if (ns > 0) {
         DISPATCH_B(b, (gather_rows_kernel<B><<<std::min(1024, (ns * b + 255) / 256), 256, 0, s->stream>>>(
                           s->L.n, ns, s->send_rows.p, v, s->send_buf.p)));
@@ -225,7 +254,7 @@ int copy_owner_to_all(opmb200_solver* s, double* v)
 // multi-rank tail of a fused reduction: all-reduce the local sums, then the scalar epilogue
 int finish_reduction(opmb200_solver* s, int nd, int epi, int check_done)
 {
-    if (s->n_ranks <= 1)
+    if (s->n_ranks <= 1 || s->p2p) // p2p: the reduction kernel's last CTA did the all-reduce and the epilogue
         return OPMB200_SUCCESS;
     NCCL_TRY(ncclAllReduce(s->sums.p, s->sums.p, nd, ncclDouble, ncclSum, s->comm->comm, s->stream));
     epilogue_kernel<<<1, 1, 0, s->stream>>>(epi, s->sc.p, s->hist.p, s->sums.p, s->dot_out.p, check_done);
@@ -250,7 +279,7 @@ int launch_spmv(opmb200_solver* s, const double* x, double* y, bool scaleadd, do
     a.alpha = alpha;
     a.u = u;
     a.copy_out = copy_out;
-    a.rc = s->rctx();
+    a.rc = ndot > 0 ? s->rctx() : ReduceCtx {};
     a.epi = epi;
     a.sc = s->sc.p;
     a.hist = s->hist.p;
@@ -515,7 +544,7 @@ int init_scalars(opmb200_solver* s, double reduction)
     return OPMB200_SUCCESS;
 }
 
-VecArgs vec_args(opmb200_solver* s)
+VecArgs vec_args(opmb200_solver* s, bool reduces)
 {
     VecArgs a;
     a.len = s->len();
@@ -526,7 +555,7 @@ VecArgs vec_args(opmb200_solver* s)
     a.t = s->vt.p;
     a.y = s->vy.p;
     a.rt = s->vrt.p;
-    a.rc = s->rctx();
+    a.rc = reduces ? s->rctx() : ReduceCtx {};
     a.sc = s->sc.p;
     a.hist = s->hist.p;
     return a;
@@ -535,18 +564,17 @@ VecArgs vec_args(opmb200_solver* s)
 // one BiCGSTAB iteration (two half steps) enqueued on the stream
 int enqueue_iteration(opmb200_solver* s)
 {
-    const VecArgs va = vec_args(s);
     const int gz = 1; // Dune: y = 0 before every preconditioner application
-    vec_p_update_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);
+    vec_p_update_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, false));
     TRY(check_launch(s, "vec_p_update"));
     TRY(prec_apply(s, s->vp.p, s->vy.p, gz, 1));                       // y = W^-1 p
     TRY(op_apply(s, s->vy.p, s->vv.p, 1, s->vrt.p, EPI_H, 1));          // v = A y ; h = (rt, v)
-    vec_half1_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);          // x += alpha y ; r -= alpha v ; |r|
+    vec_half1_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, true)); // x += alpha y ; r -= alpha v ; |r|
     TRY(check_launch(s, "vec_half1"));
     TRY(finish_reduction(s, 1, EPI_NORM1, 1));
     TRY(prec_apply(s, s->vr.p, s->vy.p, gz, 1));                       // y = W^-1 r
     TRY(op_apply(s, s->vy.p, s->vt.p, 2, s->vr.p, EPI_OMEGA, 1));       // t = A y ; (t,r), (t,t)
-    vec_half2_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);          // x += omega y ; r -= omega t ; |r| ; (rt,r)
+    vec_half2_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, true)); // x += omega y ; r -= omega t ; |r| ; (rt,r)
     TRY(check_launch(s, "vec_half2"));
     TRY(finish_reduction(s, 2, EPI_NORM2, 1));
     return OPMB200_SUCCESS;
@@ -818,8 +846,8 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
     CUDA_TRY(s->hist.alloc((size_t)2 * s->maxiter + 4));
     CUDA_TRY(s->sums.alloc(4));
     CUDA_TRY(s->dot_out.alloc(4));
-    CUDA_TRY(s->counters.alloc(4));
-    CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, 4 * sizeof(unsigned int), st));
+    CUDA_TRY(s->counters.alloc(8));
+    CUDA_TRY(cudaMemsetAsync(s->counters.p, 0, 8 * sizeof(unsigned int), st));
     CUDA_TRY(s->sc.alloc(1));
     CUDA_TRY(cudaMemsetAsync(s->sc.p, 0, sizeof(Scalars), st));
     // the sweeps' dependency records are all-sentinel between applies
@@ -853,6 +881,17 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
         CUDA_TRY(s->recv_rows.upload(rp, st));
         CUDA_TRY(s->send_buf.alloc(sp.size() * block_size));
         CUDA_TRY(s->recv_buf.alloc(rp.size() * block_size));
+        if (nn > kMaxNeighbors || s->n_ranks > kMaxRanks)
+            return fail(OPMB200_INVALID_ARGUMENT, "too many ranks / neighbours for the peer-to-peer tables");
+        // peer-to-peer arena (used once opmb200_p2p_import has mapped the peers)
+        auto align = [](size_t x) { return (x + 255) & ~(size_t)255; };
+        s->off_mbox = 0;
+        s->off_recv = align(s->off_mbox + (size_t)2 * s->n_ranks * 4 * sizeof(double));
+        s->off_dflag = align(s->off_recv + rp.size() * block_size * sizeof(double));
+        s->off_ack = align(s->off_dflag + (size_t)kMaxNeighbors * sizeof(int));
+        const size_t arena_bytes = align(s->off_ack + (size_t)kMaxNeighbors * sizeof(int));
+        CUDA_TRY(s->arena.alloc(arena_bytes));
+        CUDA_TRY(cudaMemsetAsync(s->arena.p, 0, arena_bytes, st));
     }
     if (s->schedule == 1) {
         DISPATCH_B(block_size, {
@@ -1099,7 +1138,6 @@ int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, doubl
     h.maxiter = 1 << 30;
     h.reduction = 0;
     CUDA_TRY(cudaMemcpyAsync(s->sc.p, &h, sizeof h, cudaMemcpyHostToDevice, s->stream));
-    const VecArgs va = vec_args(s);
     if (what == 3) { // non-trivial data so that no epilogue declares convergence
         for (double* v : {s->vr.p, s->vp.p, s->vv.p, s->vt.p, s->vy.p, s->vrt.p, s->vx.p}) {
             fill_kernel<<<s->vec_grid, 256, 0, s->stream>>>(v, s->len(), 1.0);
@@ -1154,9 +1192,9 @@ int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, doubl
             bytes = 2 * nnzb * blk + 16 * b * b * N;
             break;
         case 3:
-            vec_p_update_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);
-            vec_half1_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);
-            vec_half2_kernel<<<s->vec_grid, 256, 0, s->stream>>>(va);
+            vec_p_update_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, false));
+            vec_half1_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, true));
+            vec_half2_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, true));
             s->launches += 2;
             TRY(check_launch(s, "vector kernels"));
             bytes = 17 * 8 * b * N;
@@ -1187,6 +1225,98 @@ int opmb200_prof_read(unsigned long long* out16, int reset)
     return 0;
 }
 #endif
+
+namespace {
+struct P2PBlob {
+    cudaIpcMemHandle_t handle;
+    int rank, nn;
+    int peer[kMaxNeighbors];
+    long long recv_off[kMaxNeighbors], dflag_off[kMaxNeighbors], ack_off[kMaxNeighbors];
+    long long mbox_off;
+};
+static_assert(sizeof(P2PBlob) <= OPMB200_P2P_BLOB_BYTES, "blob too large");
+} // namespace
+
+int opmb200_p2p_export(opmb200_solver* s, void* blob)
+{
+    if (!s || !blob)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (s->n_ranks <= 1 || !s->arena.p)
+        return fail(OPMB200_INVALID_ARGUMENT, "peer-to-peer mode needs a communicator");
+    P2PBlob b;
+    std::memset(&b, 0, sizeof b);
+    CUDA_TRY(cudaIpcGetMemHandle(&b.handle, s->arena.p));
+    b.rank = s->comm->rank;
+    b.nn = (int)s->nb_rank.size();
+    for (int k = 0; k < b.nn; ++k) {
+        b.peer[k] = s->nb_rank[k];
+        b.recv_off[k] = (long long)(s->off_recv + (size_t)s->recv_ptr[k] * s->b * sizeof(double));
+        b.dflag_off[k] = (long long)(s->off_dflag + (size_t)k * sizeof(int));
+        b.ack_off[k] = (long long)(s->off_ack + (size_t)k * sizeof(int));
+    }
+    b.mbox_off = (long long)s->off_mbox;
+    std::memset(blob, 0, OPMB200_P2P_BLOB_BYTES);
+    std::memcpy(blob, &b, sizeof b);
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_p2p_import(opmb200_solver* s, const void* blobs)
+{
+    if (!s || !blobs)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (s->n_ranks <= 1 || !s->arena.p)
+        return fail(OPMB200_INVALID_ARGUMENT, "peer-to-peer mode needs a communicator");
+    const int me = s->comm->rank, P = s->n_ranks;
+    std::vector<P2PBlob> all(P);
+    for (int p = 0; p < P; ++p)
+        std::memcpy(&all[p], static_cast<const unsigned char*>(blobs) + (size_t)p * OPMB200_P2P_BLOB_BYTES, sizeof(P2PBlob));
+    std::vector<unsigned char*> base(P, nullptr);
+    s->peer_base.assign(P, nullptr);
+    for (int p = 0; p < P; ++p) {
+        if (all[p].rank != p)
+            return fail(OPMB200_INVALID_ARGUMENT, "peer-to-peer blobs are not in rank order");
+        if (p == me) {
+            base[p] = s->arena.p;
+        } else {
+            void* ptr = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&ptr, all[p].handle, cudaIpcMemLazyEnablePeerAccess));
+            s->peer_base[p] = ptr;
+            base[p] = static_cast<unsigned char*>(ptr);
+        }
+    }
+    P2PDev dev;
+    std::memset(&dev, 0, sizeof dev);
+    dev.rank = me;
+    dev.size = P;
+    for (int p = 0; p < P; ++p)
+        dev.mbox[p] = reinterpret_cast<double*>(base[p] + all[p].mbox_off);
+    CUDA_TRY(s->p2p_dev.alloc(1));
+    CUDA_TRY(cudaMemcpy(s->p2p_dev.p, &dev, sizeof dev, cudaMemcpyHostToDevice));
+    HaloDev& h = s->halo_dev;
+    std::memset(&h, 0, sizeof h);
+    h.nn = (int)s->nb_rank.size();
+    for (int k = 0; k <= h.nn; ++k) {
+        h.send_ptr[k] = s->send_ptr[k];
+        h.recv_ptr[k] = s->recv_ptr[k];
+    }
+    for (int k = 0; k < h.nn; ++k) {
+        const int o = s->nb_rank[k];
+        int j = -1;
+        for (int i = 0; i < all[o].nn; ++i)
+            if (all[o].peer[i] == me)
+                j = i;
+        if (j < 0)
+            return fail(OPMB200_INVALID_ARGUMENT, "halo is not symmetric: rank " + std::to_string(o) + " does not list me");
+        h.peer_recv[k] = reinterpret_cast<double*>(base[o] + all[o].recv_off[j]);
+        h.peer_dflag[k] = reinterpret_cast<int*>(base[o] + all[o].dflag_off[j]);
+        h.peer_ack[k] = reinterpret_cast<int*>(base[o] + all[o].ack_off[j]);
+    }
+    h.my_recv = reinterpret_cast<const double*>(s->arena.p + s->off_recv);
+    h.my_dflag = reinterpret_cast<int*>(s->arena.p + s->off_dflag);
+    h.my_ack = reinterpret_cast<int*>(s->arena.p + s->off_ack);
+    s->p2p = true;
+    return OPMB200_SUCCESS;
+}
 
 int opmb200_timer_start(opmb200_solver* s)
 {

@@ -318,6 +318,16 @@ class FlexibleSolver:
         _lib.check(_lib.lib().opmb200_time_kernel(self._h, what, warmup, reps, C.byref(ms), C.byref(nbytes)))
         return ms.value, nbytes.value
 
+    def enable_p2p(self, allgather):
+        """switch the collectives from NCCL to the library's own peer-memory kernels.
+        `allgather(bytes) -> list[bytes]` gathers one blob per rank in rank order
+        (torch.distributed.all_gather_object here, MPI_Allgather in Flow)."""
+        blob = C.create_string_buffer(1024)
+        _lib.check(_lib.lib().opmb200_p2p_export(self._h, C.cast(blob, C.c_void_p)))
+        blobs = b"".join(allgather(blob.raw))
+        buf = C.create_string_buffer(blobs, len(blobs))
+        _lib.check(_lib.lib().opmb200_p2p_import(self._h, C.cast(buf, C.c_void_p)))
+
     def timer_start(self):
         _lib.check(_lib.lib().opmb200_timer_start(self._h))
 

@@ -32,9 +32,12 @@ def _ngpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("collectives", ["nccl", "p2p"])
 @pytest.mark.parametrize("prec,b", [("dilu", 3), ("ilu0", 3), ("dilu", 4)])
-def test_two_rank_nccl_block_jacobi(prec, b):
+def test_two_rank_block_jacobi(prec, b, collectives):
+    """halo exchange + all-reduce over NCCL, and over the library's own peer-memory kernels"""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    r = launch(2, ["--mode", "gpu", "--prec", prec, "--b", str(b)], 29620 + b)
+    r = launch(2, ["--mode", "gpu", "--prec", prec, "--b", str(b), "--collectives", collectives],
+               29620 + b + (10 if collectives == "p2p" else 0))
     assert r.returncode == 0 and "MGPU_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
