@@ -932,53 +932,142 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
     const int S = (int)chunk * kWarpsPerCta + (threadIdx.x >> 5);
     if (S < a.nslices) {
         const SliceMeta m = a.slices[S];
+        {   // pull this slice's blocks (one contiguous region) into the L2 while the warp waits
+            const char* region = reinterpret_cast<const char*>(a.F + (size_t)m.base * 32 * BB);
+            const int lines = (m.wl + 1 + m.wu) * 32 * BB * 8 / 128;
+            for (int l = lane; l < lines; l += 32)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(region + (size_t)l * 128));
+        }
         if (lane < m.count) {
             const int q = m.q0 + lane;
+            // Fast path (7-point-like rows): at most kPrefetch lower blocks, each of which updates only
+            // the diagonal.  Everything is gathered with a few batched loads: own blocks before the
+            // wait, the neighbours' Dinv_j and U_ji after it.
+            bool fast = m.wl <= kPrefetch;
+            int cj[kPrefetch], tsrc[kPrefetch];
+            const int gdiag = (m.base + m.wl) * 32 + lane;
+#pragma unroll
+            for (int k = 0; k < kPrefetch; ++k) {
+                cj[k] = -1;
+                tsrc[k] = -1;
+                if (fast && k < m.wl) {
+                    cj[k] = a.slot_col[(size_t)(m.base + k) * 32 + lane];
+                    if (cj[k] >= 0) {
+                        const size_t cl = (size_t)(m.lrank + k) * 32 + lane;
+                        const int t0 = a.trip_ptr[cl], t1 = a.trip_ptr[cl + 1];
+                        if (t1 - t0 > 1 || (t1 - t0 == 1 && a.trip_dst[t0] != gdiag))
+                            fast = false;
+                        else if (t1 - t0 == 1)
+                            tsrc[k] = a.trip_src[t0];
+                    }
+                }
+            }
+            if (fast) {
+                double Aij[kPrefetch][BB], D[BB];
+#pragma unroll
+                for (int k = 0; k < kPrefetch; ++k)
+                    if (cj[k] >= 0) {
+#pragma unroll
+                        for (int e = 0; e < BB; ++e)
+                            Aij[k][e] = a.F[elem_index<BB>(m.base + k, lane, e)];
+                    }
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    D[e] = a.F[elem_index<BB>(m.base + m.wl, lane, e)];
+#pragma unroll
+                for (int k = 0; k < kPrefetch; ++k)
+                    if (cj[k] >= 0)
+                        while (ld_relaxed(a.row_flag + cj[k]) != a.epoch) {}
+                __threadfence();
+                double Dj[kPrefetch][BB], Uji[kPrefetch][BB];
+#pragma unroll
+                for (int k = 0; k < kPrefetch; ++k)
+                    if (cj[k] >= 0) {
+#pragma unroll
+                        for (int e = 0; e < BB; ++e) {
+                            Dj[k][e] = __ldcg(a.dinv + (size_t)cj[k] * BB + e);
+                            Uji[k][e] = tsrc[k] >= 0 ? __ldcg(a.F + elem_index_slot<BB>(tsrc[k], e)) : 0.0;
+                        }
+                    }
+#pragma unroll
+                for (int k = 0; k < kPrefetch; ++k)
+                    if (cj[k] >= 0) {
+                        double Lij[BB], P[BB];
+                        blk_mm<B>(Aij[k], Dj[k], Lij);
+#pragma unroll
+                        for (int e = 0; e < BB; ++e)
+                            a.F[elem_index<BB>(m.base + k, lane, e)] = Lij[e];
+                        if (tsrc[k] >= 0) {
+                            blk_mm<B>(Lij, Uji[k], P);
+#pragma unroll
+                            for (int e = 0; e < BB; ++e)
+                                D[e] -= P[e];
+                        }
+                    }
+                if (!blk_invert<B>(D))
+                    a.sc->factor_error = 1;
+#pragma unroll
+                for (int e = 0; e < BB; ++e) {
+                    a.F[elem_index<BB>(m.base + m.wl, lane, e)] = D[e];
+                    a.dinv[(size_t)q * BB + e] = D[e];
+                    a.dinv_s[((size_t)S * BB + e) * 32 + lane] = D[e];
+                }
+                __threadfence();
+                st_relaxed(a.row_flag + q, a.epoch);
+                goto row_done;
+            }
+            // 1. all rows this row eliminates with must be complete: poll their flags (strong loads),
+            //    then ONE acquire fence; everything after it may use ordinary L2 loads
+            for (int s = 0; s < m.wl; ++s) {
+                const int c = a.slot_col[(size_t)(m.base + s) * 32 + lane];
+                if (c >= 0)
+                    while (ld_relaxed(a.row_flag + c) != a.epoch) {}
+            }
+            __threadfence();
+            // 2. eliminate left to right; this row's own blocks are touched by this thread only
             for (int s = 0; s < m.wl; ++s) {
                 const int c = a.slot_col[(size_t)(m.base + s) * 32 + lane];
                 if (c < 0)
                     continue;
                 double Aij[BB], Dj[BB], Lij[BB];
 #pragma unroll
-                for (int e = 0; e < BB; ++e)
-                    Aij[e] = ld_relaxed(a.F + elem_index<BB>(m.base + s, lane, e));
-                wait_row<BB>(a.row_flag + c, a.epoch);
-#pragma unroll
-                for (int e = 0; e < BB; ++e)
-                    Dj[e] = ld_relaxed(a.dinv + (size_t)c * BB + e);
+                for (int e = 0; e < BB; ++e) {
+                    Aij[e] = a.F[elem_index<BB>(m.base + s, lane, e)];
+                    Dj[e] = __ldcg(a.dinv + (size_t)c * BB + e);
+                }
                 blk_mm<B>(Aij, Dj, Lij); // L_ij = A_ij A_jj^-1   (rightmultiply, :63)
 #pragma unroll
                 for (int e = 0; e < BB; ++e)
-                    st_relaxed(a.F + elem_index<BB>(m.base + s, lane, e), Lij[e]);
+                    a.F[elem_index<BB>(m.base + s, lane, e)] = Lij[e];
                 const size_t cl = (size_t)(m.lrank + s) * 32 + lane;
                 for (int t = a.trip_ptr[cl]; t < a.trip_ptr[cl + 1]; ++t) { // A_ik -= L_ij A_jk (:66-86)
                     const int gs = a.trip_src[t], gd = a.trip_dst[t];
                     double Ujk[BB], P[BB];
 #pragma unroll
                     for (int e = 0; e < BB; ++e)
-                        Ujk[e] = ld_relaxed(a.F + elem_index_slot<BB>(gs, e));
+                        Ujk[e] = __ldcg(a.F + elem_index_slot<BB>(gs, e));
                     blk_mm<B>(Lij, Ujk, P);
 #pragma unroll
-                    for (int e = 0; e < BB; ++e) {
-                        double* p = a.F + elem_index_slot<BB>(gd, e);
-                        st_relaxed(p, ld_relaxed(p) - P[e]);
-                    }
+                    for (int e = 0; e < BB; ++e)
+                        a.F[elem_index_slot<BB>(gd, e)] -= P[e];
                 }
             }
             double D[BB];
 #pragma unroll
             for (int e = 0; e < BB; ++e)
-                D[e] = ld_relaxed(a.F + elem_index<BB>(m.base + m.wl, lane, e));
+                D[e] = a.F[elem_index<BB>(m.base + m.wl, lane, e)];
             if (!blk_invert<B>(D))
                 a.sc->factor_error = 1;
 #pragma unroll
             for (int e = 0; e < BB; ++e) {
-                st_relaxed(a.F + elem_index<BB>(m.base + m.wl, lane, e), D[e]);
-                st_relaxed(a.dinv + (size_t)q * BB + e, D[e]);
+                a.F[elem_index<BB>(m.base + m.wl, lane, e)] = D[e];
+                a.dinv[(size_t)q * BB + e] = D[e];
                 a.dinv_s[((size_t)S * BB + e) * 32 + lane] = D[e];
             }
+            // 3. publish: release fence, then the flag
             __threadfence();
             st_relaxed(a.row_flag + q, a.epoch);
+        row_done:;
         }
     }
     return_ticket(a.ticket);
