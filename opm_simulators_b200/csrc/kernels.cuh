@@ -1414,7 +1414,7 @@ __global__ void __launch_bounds__(kChunkWarps * 32, 1) chunk_sweep_kernel(ChunkS
         // request the staged part of slice t: block values and columns of its first kPrefetch slot
         // rows, and its Dinv
         auto request = [&](int t) {
-            if (t < ns && lane == 0) {
+            if (t < ns && lane == 0 && !(a.debug & 8)) {
                 const SliceMeta m = metas[t % kMetaWin];
                 const int st = t % NS;
                 unsigned char* sb = stage0 + (size_t)st * SM::kStageBytes;
@@ -1447,9 +1447,13 @@ __global__ void __launch_bounds__(kChunkWarps * 32, 1) chunk_sweep_kernel(ChunkS
                 cj[s] = (lane < m.count && s < width(m)) ? cols[s * 32 + lane] : -1;
 #pragma unroll
             for (int s = 0; s < kPrefetch; ++s)
-                if (cj[s] >= 0 && !in_ring(cj[s], m))
+                if (cj[s] >= 0 && !in_ring(cj[s], m) && !(a.debug & 4))
                     rec_load_strong<B>(out, (size_t)cj[s], ext[s]);
-            if (lane < m.count) {
+            if (a.debug & 4) {
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    in[r] = 1.0;
+            } else if (lane < m.count) {
                 if (UPPER) {
                     rec_load_strong<B>(a.tmp, (size_t)q, in);
                 } else {
@@ -1467,7 +1471,8 @@ __global__ void __launch_bounds__(kChunkWarps * 32, 1) chunk_sweep_kernel(ChunkS
         double extA[kPrefetch][B], extB[kPrefetch][B], inA[B], inB[B];
         bool haveA = false;
         if (ns > 0) {
-            mbar_wait(bars + 0, 0);
+            if (!(a.debug & 8))
+                mbar_wait(bars + 0, 0);
             load_ahead(0, cjA, extA, inA);
             haveA = true;
         }
@@ -1491,7 +1496,8 @@ __global__ void __launch_bounds__(kChunkWarps * 32, 1) chunk_sweep_kernel(ChunkS
             request(t + NS - 1); // its stage was released at the end of step t-1
             PROF_MARK(0);
             if (!haveA) {
-                mbar_wait(bars + st, parity);
+                if (!(a.debug & 8))
+                    mbar_wait(bars + st, parity);
                 load_ahead(t, cjA, extA, inA);
             }
             PROF_MARK(1);
@@ -1499,7 +1505,7 @@ __global__ void __launch_bounds__(kChunkWarps * 32, 1) chunk_sweep_kernel(ChunkS
             const double* sdinv = reinterpret_cast<const double*>(stage0 + (size_t)st * SM::kStageBytes + SM::kBlkBytes);
 
             // look ahead one slice if its stage has already landed (it was requested NS-1 steps ago)
-            bool haveB = (t + 1 < ns) && mbar_try_wait(bars + (t + 1) % NS, (unsigned)((t + 1) / NS) & 1u);
+            bool haveB = (t + 1 < ns) && ((a.debug & 8) || mbar_try_wait(bars + (t + 1) % NS, (unsigned)((t + 1) / NS) & 1u));
             haveB = __all_sync(0xffffffffu, haveB);
             if (haveB)
                 load_ahead(t + 1, cjB, extB, inB);
