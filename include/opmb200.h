@@ -111,6 +111,18 @@ int opmb200_set_device(int device);
  * color[n], level_rows[n], level_ptr[n+1] (first *n_levels+1 entries valid). */
 int opmb200_row_coloring(int64_t n, const int32_t* rowptr, const int32_t* colidx, int type,
                          int32_t* color, int32_t* level_rows, int32_t* level_ptr, int32_t* n_levels);
+/* The sweep schedule of a sparsity pattern, host only (what opmb200_create builds; the threaded
+ * reference orders rows by level set, DILU.hpp:82-91, 306-363).  schedule 0 = level sets, 1 = chunked
+ * wavefronts (chunk_rows > 0 forces contiguous chunks of that many rows, <= 0 chooses; box grids get
+ * tiles of 32 grid lines, reported as chunk_rows = -(TJ*100+TK)).  position_to_row[n]: rows in
+ * schedule order; slice_first[n+1] (first *n_slices+1 valid): first position of every 32-row slice
+ * (= one step of one warp); chunk_first_slice[n+2] (first *n_chunks+1 valid; schedule 1 only).
+ * Invariant the sweeps rely on: a row depends only on rows of earlier slices, and only on rows of
+ * the same or an earlier chunk.  Output pointers may be NULL. */
+int opmb200_plan_schedule(int block_size, int64_t n_rows, int64_t nnzb, const int32_t* rowptr, const int32_t* colidx,
+                          int64_t n_interior, int schedule, int chunk_rows, int32_t* n_slices, int32_t* n_chunks,
+                          int32_t* chunk_rows_out, double* est_steps, int32_t* position_to_row, int32_t* slice_first,
+                          int32_t* chunk_first_slice);
 /* Opm::partitionCellsSimple (opm/simulators/flow/partitionCells.cpp:734-751) */
 int opmb200_partition_simple(int32_t num_cells, int32_t num_domains, int32_t* part);
 /* Ghost-last local system of one rank with one overlap layer (FlowGenericVanguard.hpp:79,

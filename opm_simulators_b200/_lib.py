@@ -55,6 +55,9 @@ PROTOTYPES = {
     "opmb200_device_count": (C.c_int, [C.POINTER(C.c_int)]),
     "opmb200_set_device": (C.c_int, [C.c_int]),
     "opmb200_row_coloring": (C.c_int, [C.c_int64, _i32p, _i32p, C.c_int, _i32p, _i32p, _i32p, C.POINTER(C.c_int32)]),
+    "opmb200_plan_schedule": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _i32p, _i32p, C.c_int64, C.c_int, C.c_int,
+                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                         C.POINTER(C.c_double), _vp, _vp, _vp]),
     "opmb200_partition_simple": (C.c_int, [C.c_int32, C.c_int32, _i32p]),
     "opmb200_localize": (C.c_int, [C.c_int64, _i32p, _i32p, _i32p, C.c_int32, C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, _vp, _vp, _vp]),

@@ -89,28 +89,69 @@ struct ChunkPlan {
     double total_steps = 0;
 };
 
-template <class RowBegin, class RowEnd>
-void plan_chunks(int64_t n, int64_t n_interior, const int32_t* col, const std::vector<int32_t>& glev,
-                 RowBegin row_begin, RowEnd row_end, int64_t R, double t_ext, ChunkPlan& P)
+// chunk ids of contiguous runs of R rows of the natural ordering.  A chunk ends after R rows, at the
+// owner/ghost border, and wherever the wavefront restarts: a row whose global level lies below the
+// level of the chunk's first row could have started before this chunk did, so queueing it behind
+// the chunk would serialise independent work (on a box grid: the first row of the next plane
+// behind the last strip of the current plane).
+int32_t contiguous_chunks(int64_t n, int64_t n_interior, const std::vector<int32_t>& glev, int64_t R,
+                          std::vector<int32_t>& chunk_id)
 {
-    // A chunk is a contiguous run of rows of the natural ordering.  It ends after R rows, at the
-    // owner/ghost border, and wherever the wavefront restarts: a row whose global level lies below
-    // the level of the chunk's first row could have started before this chunk did, so queueing it
-    // behind the chunk would serialise independent work (on a box grid: the first row of the next
-    // plane behind the last strip of the current plane).
-    std::vector<int32_t> chunk_id(n);
-    {
-        int32_t c = -1;
-        int64_t begin = 0;
-        for (int64_t i = 0; i < n; ++i) {
-            if (i == 0 || i - begin >= R || i == n_interior || glev[i] < glev[begin]) {
-                ++c;
-                begin = i;
-            }
-            chunk_id[i] = c;
+    chunk_id.resize(n);
+    int32_t c = -1;
+    int64_t begin = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (i == 0 || i - begin >= R || i == n_interior || glev[i] < glev[begin]) {
+            ++c;
+            begin = i;
         }
-        P.n_chunks = c + 1;
+        chunk_id[i] = c;
     }
+    return c + 1;
+}
+
+// chunk ids of TJ x TK tiles of grid lines on a box grid in natural order (nx cells per line, ny
+// lines per plane): 32 lines per chunk, one per lane, so that the j-1 AND the k-1 neighbour of most
+// rows are served by the chunk's own ring; tiles are numbered plane-band by plane-band.  Ghost
+// rows (>= n_interior) get contiguous chunks behind the tiles.  The caller validates the result
+// (chunk_order_valid): the pattern need not be a clean 7-point stencil.
+int32_t tile_chunks(int64_t n, int64_t n_interior, int64_t nx, int64_t ny, int TJ, int TK, std::vector<int32_t>& chunk_id)
+{
+    chunk_id.resize(n);
+    const int64_t nxy = nx * ny;
+    const int64_t ntj = (ny + TJ - 1) / TJ;
+    int32_t nc = 0;
+    for (int64_t i = 0; i < n_interior; ++i) {
+        const int64_t k = i / nxy, j = (i % nxy) / nx;
+        chunk_id[i] = (int32_t)((k / TK) * ntj + j / TJ);
+        nc = std::max(nc, chunk_id[i] + 1);
+    }
+    for (int64_t i = n_interior; i < n; ++i)
+        chunk_id[i] = nc + (int32_t)((i - n_interior) / 1024);
+    if (n > n_interior)
+        nc = chunk_id[n - 1] + 1;
+    return nc;
+}
+
+// every dependency must point to the same or an earlier chunk (lower sweep; the upper sweep walks
+// the chunks backwards), otherwise in-order chunk start could deadlock
+template <class RowBegin, class RowEnd>
+bool chunk_order_valid(int64_t n, const int32_t* col, const std::vector<int32_t>& chunk_id, RowBegin row_begin, RowEnd row_end)
+{
+    for (int64_t r = 0; r < n; ++r)
+        for (int64_t k = row_begin(r); k < row_end(r); ++k) {
+            const int32_t c = col[k];
+            if ((c < r && chunk_id[c] > chunk_id[r]) || (c > r && chunk_id[c] < chunk_id[r]))
+                return false;
+        }
+    return true;
+}
+
+template <class RowBegin, class RowEnd>
+void plan_chunks(int64_t n, const int32_t* col, const std::vector<int32_t>& chunk_id, int32_t n_chunks,
+                 RowBegin row_begin, RowEnd row_end, double t_ext, ChunkPlan& P)
+{
+    P.n_chunks = n_chunks;
     auto chunk_of = [&](int64_t i) { return (int64_t)chunk_id[i]; };
     std::vector<int32_t> llev(n, 0);
     for (int64_t r = 0; r < n; ++r) {
@@ -265,9 +306,11 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
         ChunkPlan best;
         const double t_ext = 4.0, resident = 1184.0;
         std::vector<int64_t> cands;
+        int64_t line = 0, plane = 0; // nx and nx*ny of a box grid in natural order (0: not recognised)
         if (chunk_rows > 0) {
             cands.push_back(chunk_rows);
-        } else {
+        }
+        if (chunk_rows <= 0) {
             // "line length" of the ordering = the most frequent lower offset larger than 1 (nx on a
             // box grid): chunks of 32 lines fill the 32 lanes of a slice best
             std::vector<int64_t> offs;
@@ -277,7 +320,7 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
                     if (col[k] < r - 1)
                         offs.push_back(r - col[k]);
             std::sort(offs.begin(), offs.end());
-            int64_t line = 0, bestc = 0;
+            int64_t bestc = 0, bestp = 0;
             for (size_t i = 0; i < offs.size();) {
                 size_t j = i;
                 while (j < offs.size() && offs[j] == offs[i])
@@ -289,14 +332,26 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
                 }
                 i = j;
             }
+            for (size_t i = 0; i < offs.size();) { // plane offset: the most frequent offset beyond the line offset
+                size_t j = i;
+                while (j < offs.size() && offs[j] == offs[i])
+                    ++j;
+                if (offs[i] > line && (int64_t)(j - i) > bestp + bestp / 4) {
+                    bestp = (int64_t)(j - i);
+                    plane = offs[i];
+                }
+                i = j;
+            }
+            if (bestp * 4 < bestc)
+                plane = 0;
             for (int64_t R : {(int64_t)1024, (int64_t)2048, (int64_t)4096, (int64_t)8192, 16 * line, 32 * line, 64 * line})
-                if (R >= 256 && R <= 65536 && std::find(cands.begin(), cands.end(), R) == cands.end())
+                if (chunk_rows == 0 && R >= 256 && R <= 65536 && std::find(cands.begin(), cands.end(), R) == cands.end())
                     cands.push_back(R);
         }
         double best_cost = -1;
-        for (int64_t R : cands) {
+        auto consider = [&](const std::vector<int32_t>& chunk_id, int32_t nc, int64_t R) {
             ChunkPlan P;
-            plan_chunks(n, n_interior, col, lev, row_begin, row_end, R, t_ext, P);
+            plan_chunks(n, col, chunk_id, nc, row_begin, row_end, t_ext, P);
             const double padding = P.total_steps * kSlice / (double)std::max<int64_t>(n, 1);
             const double cost = std::max(P.est_steps, P.total_steps / resident) + 200.0 * std::max(0.0, padding - 1.6);
             if (best_cost < 0 || cost < best_cost) {
@@ -304,6 +359,27 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
                 best = std::move(P);
                 L.chunk_rows = (int)R;
             }
+        };
+        std::vector<int32_t> chunk_id;
+        for (int64_t R : cands) {
+            const int32_t nc = contiguous_chunks(n, n_interior, lev, R, chunk_id);
+            consider(chunk_id, nc, R);
+        }
+        // box grids: tiles of 32 grid lines (chunk_rows reports -(TJ*100 + TK); a negative request
+        // forces that tile shape)
+        if (chunk_rows <= 0 && line > 1 && plane > line && plane % line == 0) {
+            for (int TK : {2, 4, 8}) {
+                const int TJ = 32 / TK;
+                if (chunk_rows < 0 && chunk_rows != -(TJ * 100 + TK))
+                    continue;
+                const int32_t nc = tile_chunks(n, n_interior, line, plane / line, TJ, TK, chunk_id);
+                if (chunk_order_valid(n, col, chunk_id, row_begin, row_end))
+                    consider(chunk_id, nc, -(TJ * 100 + TK));
+            }
+        }
+        if (best_cost < 0) { // a forced tile shape that the pattern does not admit: contiguous chunks
+            const int32_t nc = contiguous_chunks(n, n_interior, lev, 2048, chunk_id);
+            consider(chunk_id, nc, 2048);
         }
         lev = best.grp; // group id replaces the level from here on
         nlev = best.n_groups;
@@ -405,6 +481,38 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
                 L.slot_col[g] = L.n2r[col[k]];
                 L.slot_src[g] = (int32_t)k;
                 slot_of_native[k] = (int32_t)g;
+            }
+        }
+    }
+
+    // ---- chunk sweeps: which dependencies the shared-memory ring of a chunk serves ------------------
+    L.sweep_col.clear();
+    if (schedule_mode == 1) {
+        constexpr int32_t kRingValid = 96, kRingFlag = 1 << 30; // kernels.cuh
+        if (n >= (int64_t)kRingFlag) {
+            err = "matrix too large for the chunk schedule";
+            return OPMB200_INVALID_ARGUMENT;
+        }
+        L.sweep_col = L.slot_col;
+        for (int32_t c = 0; c < L.n_chunks; ++c) {
+            const int32_t q_lo = L.slice_q0[L.chunk_slice0[c]], q_hi = L.slice_q0[L.chunk_slice0[c + 1]];
+            for (int s = L.chunk_slice0[c]; s < L.chunk_slice0[c + 1]; ++s) {
+                const int32_t q0 = L.slice_q0[s], q1 = L.slice_q0[s + 1];
+                const int64_t base = L.slice_base[s];
+                const int wl = L.slice_wl[s], wu = L.slice_wu[s];
+                for (int sr = 0; sr < wl + 1 + wu; ++sr) {
+                    if (sr == wl)
+                        continue;
+                    for (int lane = 0; lane < q1 - q0; ++lane) {
+                        int32_t& p = L.sweep_col[(base + sr) * kSlice + lane];
+                        if (p < 0)
+                            continue;
+                        const bool ring = sr < wl ? (p < q0 && p >= q0 - kRingValid && p >= q_lo)
+                                                  : (p >= q1 && p < q1 + kRingValid && p < q_hi);
+                        if (ring)
+                            p |= kRingFlag;
+                    }
+                }
             }
         }
     }

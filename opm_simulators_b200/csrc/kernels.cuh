@@ -1262,45 +1262,68 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
 // chunked-wavefront sweeps (schedule mode "chunks")
 //
 // A producer->consumer hop through the L2 costs 500-1000+ cycles, a hop that stays inside a warp
-// ~100.  Here ONE WARP walks ONE CHUNK (a contiguous run of rows of the natural ordering, its rows
-// ordered by chunk-local level) slice after slice:
+// ~100.  Here ONE COMPUTE WARP walks ONE CHUNK (a contiguous run of rows of the natural ordering,
+// its rows ordered by chunk-local level) step after step (step = one 32-row slice):
 //   * dependencies on rows of the same chunk are served from a shared-memory ring of the last 96
-//     results; only dependencies that cross a chunk boundary are polled in the L2 (dependency
-//     records + sentinel, as above), and those polls are issued one slice ahead, so a producer
-//     that is already done costs no round trip;
-//   * the matrix stream of a chunk (block values, column positions, Dinv) is contiguous; it is
-//     pulled into a per-warp shared-memory ring of kStages slices with TMA bulk copies
-//     (cp.async.bulk -> UBLKCP) that complete on per-stage mbarriers, so no load latency is
-//     exposed inside a step: the warp only ever waits for a stage that was requested kStages-1
-//     steps earlier.
+//     results (the analysis marks those slots with kRingFlag in `sweep_col`); only dependencies
+//     that cross a chunk boundary are sampled in the L2 (dependency records + sentinel, as in
+//     sweep_kernel), and they are sampled one step ahead, so a producer that is already done
+//     costs no round trip;
+//   * every compute warp has a LOADER warp (one lane of it works): each step's matrix data (header,
+//     column positions, block values, Dinv) is ONE contiguous record of a per-sweep stream
+//     (cw_stream_fill_kernel), so the loader's step is: wait on the stage's "empty" mbarrier,
+//     arm its "full" mbarrier, issue one TMA bulk copy (cp.async.bulk -> UBLKCP) from a pointer
+//     it increments.  A loader that has to compute addresses or issue several copies per step
+//     (~200 instructions on a lone thread ~ 1000 cycles) is slower than the compute warp and
+//     becomes the step time -- measured.  The compute warp executes no address arithmetic and no
+//     TMA issue: its step is ~one basic block of LDS + DFMA + 2-4 stores.
 // -------------------------------------------------------------------------------------------------
-constexpr int kChunkWarps = 4;
-constexpr int kRing = 128;      // ring positions per warp
-constexpr int kRingValid = 96;  // how far back the ring may be read (kRing - 32: no aliasing with writes)
-constexpr int kMetaWin = 64;    // slice metas staged in shared memory per warp
+constexpr int kCwWarps = 4;        // compute warps per CTA (and as many loader warps)
+constexpr int kRing = 128;         // ring positions per compute warp
+constexpr int kRingValid = 96;     // how far back the ring may be read (kRing - 32: no aliasing with the step's writes)
+constexpr int kRingFlag = 1 << 30; // sweep_col: the dependency is served by the ring
+constexpr int kCwHasExt = 1 << 16; // step header, width word: some row of the step has a dependency outside the ring
 
 template <int B>
-struct ChunkSmem {
+struct CwSmem {
     static constexpr int BB = B * B;
-    static constexpr int kStages = (B <= 3) ? 4 : 2;
-    static constexpr int kBlkBytes = kPrefetch * 32 * BB * 8;
-    static constexpr int kDinvBytes = 32 * BB * 8;
-    static constexpr int kColBytes = kPrefetch * 32 * 4;
-    static constexpr int kStageBytes = kBlkBytes + kDinvBytes + kColBytes; // multiple of 128
+    static constexpr int kStages = (B <= 3) ? 5 : 3;
+    static constexpr int kHdrOff = 0;                         // int4 {q0, count, width | kCwHasExt, first slot row}
+    static constexpr int kColOff = 128;                       // kPrefetch x 32 column positions (+ kRingFlag)
+    // block values element-major like the SELL slots: element e of lane l at (e*32 + l)*8
+    // (a pair layout read with LDS.128 was measured: fewer instructions, same step time)
+    static constexpr int kSlotBytes = BB * 32 * 8;
+    static constexpr int kBlkOff = kColOff + kPrefetch * 128; // kPrefetch block slots
+    static constexpr int kBlkBytes = kPrefetch * kSlotBytes;
+    static constexpr int kDinvOff = kBlkOff + kBlkBytes;
+    static constexpr int kDinvBytes = kSlotBytes;
+    static constexpr int kStageBytes = kDinvOff + kDinvBytes; // multiple of 128
+    static constexpr int kRingOff = kStages * kStageBytes;
     static constexpr int kRingBytes = kRing * B * 8;
-    static constexpr int kMetaBytes = kMetaWin * (int)sizeof(SliceMeta);
-    static constexpr int kBarBytes = 64; // kStages mbarriers
-    static constexpr int kWarpBytes = kStages * kStageBytes + kRingBytes + kMetaBytes + kBarBytes;
-    static constexpr int kCtaBytes = kChunkWarps * kWarpBytes;
+    static constexpr int kBarOff = kRingOff + kRingBytes; // kStages "full" mbarriers, then the progress counter
+    static constexpr int kProgressOff = kBarOff + 64;
+    static constexpr int kWarpBytes = kBarOff + 128;
+    static constexpr int kCtaBytes = kCwWarps * kWarpBytes;
 };
 
-struct ChunkSweepArgs {
+// One step record of a sweep stream = exactly what a stage receives: header, column positions,
+// kPrefetch slot rows of block values (zero beyond the width) and, except for the ILU0 lower sweep,
+// Dinv.  The records of a chunk are contiguous in walking order (lower: slice order; upper: reverse),
+// so the loader issues ONE bulk copy per step from a pointer it merely increments.
+template <int B>
+__host__ __device__ constexpr int cw_record_bytes(bool with_dinv)
+{
+    return CwSmem<B>::kDinvOff + (with_dinv ? CwSmem<B>::kDinvBytes : 0);
+}
+
+struct CwArgs {
     int nchunks;
     const int* chunk_slice0; // [nchunks+1]
     const SliceMeta* slices;
-    const int* slot_col;
-    const double* M;
-    const double* dinv_s; // Dinv in slice layout [slice][b*b][32]
+    const int* slot_col;  // plain column positions (rows wider than kPrefetch)
+    const unsigned char* stream; // this sweep's step records (cw_record_bytes each), in walking order
+    int nslices;
+    const double* M;      // SELL values, only for rows wider than kPrefetch
     const double* d;
     double* tmp;   // dependency records of the lower sweep's result y
     double* vpoll; // dependency records of the upper sweep's result
@@ -1308,7 +1331,8 @@ struct ChunkSweepArgs {
     const int* r2n;
     int64_t n, n_interior;
     int ghost_zero;
-    int debug; // timing experiments only: 1 = do not wait for dependencies
+    int prefetch; // L2 look-ahead of the loader warps, in steps (0..32)
+    int debug;    // OPMB200_PROFILE builds only: timing experiments that switch parts of the step off (wrong results)
     Ticket ticket;
     Scalars* sc;
     int check_done;
@@ -1331,6 +1355,10 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity)
 {
     unsigned ok;
@@ -1351,232 +1379,311 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// strong record load WITHOUT a compiler memory barrier: the look-ahead samples may be scheduled
+// freely among the shared-memory loads of the running step (they touch other rows' records only)
+template <int B>
+__device__ __forceinline__ void rec_load_ahead(const double* base, size_t q, double (&x)[B])
+{
+    const double* p = base + q * Rec<B>::W;
+    if constexpr (Rec<B>::W == 2) {
+        double w0, w1;
+        asm volatile("ld.relaxed.gpu.global.v2.f64 {%0,%1}, [%2];" : "=d"(w0), "=d"(w1) : "l"(p));
+        x[0] = w0;
+        if constexpr (B == 2)
+            x[1] = w1;
+    } else {
+        double w0, w1, w2, w3;
+        asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3) : "l"(p));
+        x[0] = w0;
+        x[1] = w1;
+        x[2] = w2;
+        if constexpr (B == 4)
+            x[3] = w3;
+    }
+}
+// weak load of a record written by an EARLIER kernel (the lower sweep's y read by the upper sweep).
+// NOT __ldcg: ld.global.cg compiles to LDG.STRONG.GPU, and the hardware serialises strong loads
+// (~330 cycles each beyond the first few in flight, scripts/microbench_hop.cu)
+template <int B>
+__device__ __forceinline__ void rec_load_weak(const double* base, size_t q, double (&x)[B])
+{
+    const double2* p = reinterpret_cast<const double2*>(base + q * Rec<B>::W);
+    const double2 a = __ldcs(p);
+    x[0] = a.x;
+    if constexpr (B >= 2)
+        x[1] = a.y;
+    if constexpr (B >= 3) {
+        const double2 b = __ldcs(p + 1);
+        x[2] = b.x;
+        if constexpr (B == 4)
+            x[3] = b.y;
+    }
+}
+
+// the BB values of lane `lane` in a block slot of a stage (shared memory)
+template <int BB>
+__device__ __forceinline__ void cw_load_slot(const unsigned char* slot, int lane, double (&v)[BB])
+{
+    const double* p = reinterpret_cast<const double*>(slot) + lane;
+#pragma unroll
+    for (int e = 0; e < BB; ++e)
+        v[e] = p[e * 32];
+}
+
+__device__ __forceinline__ bool cw_is_ring(int c) { return ((unsigned)c >> 30) == 1u; }
+__device__ __forceinline__ bool cw_is_ext(int c) { return ((unsigned)c >> 30) == 0u; }
 
 #ifdef OPMB200_PROFILE
+#define CW_DBG(bit) (a.debug & (bit))
+#else
+#define CW_DBG(bit) false
+#endif
+#ifdef OPMB200_PROFILE
+// in-kernel phase profile of the compute warps (lane 0): cycles per phase summed over all steps
 __device__ unsigned long long g_prof[16];
+__device__ unsigned long long g_chunk_t[3 * 4096]; // per chunk: resident, first step ready, done (globaltimer ns)
+__device__ __forceinline__ unsigned long long gtime()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define PROF_CHUNK(c, k)                                                                                               \
+    do {                                                                                                               \
+        if (lane == 0 && (c) < 4096)                                                                                   \
+            g_chunk_t[3 * (c) + (k)] = gtime();                                                                        \
+    } while (0)
+#define PROF_DECL long long tprev__ = clock64(); unsigned long long pacc__[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define PROF_MARK(i)                                                                                                   \
     do {                                                                                                               \
         const long long now__ = clock64();                                                                             \
-        if (lane == 0)                                                                                                 \
-            atomicAdd(&g_prof[i], (unsigned long long)(now__ - tprev__));                                              \
-        tprev__ = clock64();                                                                                           \
+        pacc__[i] += (unsigned long long)(now__ - tprev__);                                                            \
+        tprev__ = now__;                                                                                               \
+    } while (0)
+#define PROF_FLUSH(nsteps)                                                                                             \
+    do {                                                                                                               \
+        if (lane == 0) {                                                                                               \
+            for (int i__ = 0; i__ < 8; ++i__)                                                                          \
+                atomicAdd(&g_prof[i__], pacc__[i__]);                                                                  \
+            atomicAdd(&g_prof[8], (unsigned long long)(nsteps));                                                       \
+            atomicAdd(&g_prof[9], 1ull);                                                                               \
+        }                                                                                                              \
     } while (0)
 #else
+#define PROF_CHUNK(c, k)
+#define PROF_DECL
 #define PROF_MARK(i)
+#define PROF_FLUSH(nsteps)
 #endif
 
+// what a compute warp holds about a step before it runs it
+template <int B>
+struct CwStep {
+    int4 hdr;                 // q0, count, width, first slot row
+    int cj[kPrefetch];        // staged column positions (-1: none)
+    double ext[kPrefetch][B]; // sampled records of the dependencies outside the ring (0 elsewhere)
+    double in[B];             // the row's own input: d_i (lower), y_i (upper)
+};
+
+// ---- loader warp (one lane) -----------------------------------------------------------------------
 template <int B, bool ILU0, bool UPPER>
-__global__ void __launch_bounds__(kChunkWarps * 32, 1) chunk_sweep_kernel(ChunkSweepArgs a)
+__device__ __forceinline__ void cw_loader(const CwArgs& a, unsigned char* wbase, int s0, int s1)
 {
-    using SM = ChunkSmem<B>;
+    using SM = CwSmem<B>;
+    constexpr int NS = SM::kStages;
+    constexpr unsigned kRec = (unsigned)cw_record_bytes<B>(!(ILU0 && !UPPER));
+    const int ns = s1 - s0;
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(wbase + SM::kBarOff);
+    volatile int* progress = reinterpret_cast<volatile int*>(wbase + SM::kProgressOff); // steps the compute warp has finished
+    const unsigned char* src = a.stream + (size_t)(UPPER ? a.nslices - s1 : s0) * kRec;
+    const int PF = a.prefetch;
+    int st = 0;
+    int done = 0;
+    for (int t = 0; t < ns; ++t) {
+        // stage st is free once step t - NS is finished.  A plain shared-memory counter, not an
+        // "empty" mbarrier: an arrive per step on the compute warp's side costs it ~200 cycles
+        // (scripts/microbench_mbar.cu), a store costs nothing.  The compute warp's last reads of a
+        // stage feed the values it stores to its ring before it bumps the counter, so the copy
+        // issued here cannot overtake them.
+        while (done < t + 1 - NS) {
+            done = *progress;
+            if (done < t + 1 - NS)
+                __nanosleep(32);
+        }
+        mbar_expect_tx(full + st, CW_DBG(8) ? 0u : kRec);
+        if (!CW_DBG(8))
+            tma_load_1d(wbase + (size_t)st * SM::kStageBytes, src, kRec, full + st);
+        if (PF > 0 && t >= NS && t + PF < ns)
+            l2_prefetch_bulk(src + (size_t)PF * kRec, kRec); // keeps pace with the compute warp
+        src += kRec;
+        if (++st == NS)
+            st = 0;
+    }
+}
+
+// ---- compute warp ---------------------------------------------------------------------------------
+// predicated strong record load / store: one instruction, no branch (x keeps its value when !p)
+template <int B>
+__device__ __forceinline__ void rec_load_ahead_if(bool p, const double* base, size_t q, double (&x)[B])
+{
+    const double* ptr = base + q * Rec<B>::W;
+    const unsigned pr = p ? 1u : 0u;
+    if constexpr (Rec<B>::W == 2) {
+        double w0 = x[0], w1 = (B == 2) ? x[B - 1] : 0.0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.relaxed.gpu.global.v2.f64 {%0,%1}, [%2];\n\t}"
+                     : "+d"(w0), "+d"(w1)
+                     : "l"(ptr), "r"(pr));
+        x[0] = w0;
+        if constexpr (B == 2)
+            x[1] = w1;
+    } else {
+        double w0 = x[0], w1 = x[1], w2 = x[2], w3 = (B == 4) ? x[B - 1] : 0.0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];\n\t}"
+                     : "+d"(w0), "+d"(w1), "+d"(w2), "+d"(w3)
+                     : "l"(ptr), "r"(pr));
+        x[0] = w0;
+        x[1] = w1;
+        x[2] = w2;
+        if constexpr (B == 4)
+            x[3] = w3;
+    }
+}
+template <int B>
+__device__ __forceinline__ void rec_store_strong_if(bool p, double* base, size_t q, const double (&x)[B])
+{
+    double* ptr = base + q * Rec<B>::W;
+    const unsigned pr = p ? 1u : 0u;
+    if constexpr (Rec<B>::W == 2) {
+        const double w1 = (B == 2) ? x[B - 1] : 0.0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.relaxed.gpu.global.v2.f64 [%0], {%1,%2};\n\t}" ::"l"(ptr),
+                     "d"(x[0]), "d"(w1), "r"(pr)
+                     : "memory");
+    } else {
+        const double w3 = (B == 4) ? x[B - 1] : 0.0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.relaxed.gpu.global.v4.f64 [%0], {%1,%2,%3,%4};\n\t}" ::"l"(ptr),
+                     "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(w3), "r"(pr)
+                     : "memory");
+    }
+}
+template <int B>
+__device__ __forceinline__ void rec_store_sentinel_if(bool p, double* base, size_t q)
+{
+    double x[B];
+#pragma unroll
+    for (int r = 0; r < B; ++r)
+        x[r] = __longlong_as_double((long long)kSentinelBits);
+    rec_store_strong_if<B>(p, base, q, x);
+}
+
+template <int B, bool ILU0, bool UPPER>
+__device__ __forceinline__ void cw_compute(const CwArgs& a, unsigned char* wbase, int s0, int s1, int lane, int chunk)
+{
+    using SM = CwSmem<B>;
     constexpr int BB = B * B;
     constexpr int NS = SM::kStages;
     constexpr bool NEED_DINV = !(ILU0 && !UPPER);
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const unsigned int ticket = take_ticket(a.ticket);
-    const bool skip = a.check_done && a.sc->done;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cf = (int)ticket * kChunkWarps + warp;
-    if (!skip && cf < a.nchunks) {
-        unsigned char* wbase = smem_raw + (size_t)warp * SM::kWarpBytes;
-        unsigned char* stage0 = wbase;
-        double* ring = reinterpret_cast<double*>(wbase + NS * SM::kStageBytes);
-        SliceMeta* metas = reinterpret_cast<SliceMeta*>(wbase + NS * SM::kStageBytes + SM::kRingBytes);
-        unsigned long long* bars
-            = reinterpret_cast<unsigned long long*>(wbase + NS * SM::kStageBytes + SM::kRingBytes + SM::kMetaBytes);
-        const int c = UPPER ? a.nchunks - 1 - cf : cf;
-        const int s0 = a.chunk_slice0[c], s1 = a.chunk_slice0[c + 1];
-        const int ns = s1 - s0;
-        double* out = UPPER ? a.vpoll : a.tmp;
-        auto slice_id = [&](int t) { return UPPER ? s1 - 1 - t : s0 + t; };
-        auto fill_meta = [&](int t_from, int cnt) {
-            for (int k = lane; k < cnt; k += 32) {
-                const int t = t_from + k;
-                if (t < ns)
-                    metas[t % kMetaWin] = a.slices[slice_id(t)];
-            }
-        };
-        if (lane == 0)
-            for (int i = 0; i < NS; ++i)
-                mbar_init(bars + i, 1);
-        fill_meta(0, kMetaWin);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        __syncwarp();
-        const int q_lo = ns > 0 ? a.slices[s0].q0 : 0;
-        const int q_hi = ns > 0 ? a.slices[s1 - 1].q0 + a.slices[s1 - 1].count : 0;
+    const int ns = s1 - s0;
+    double* ring = reinterpret_cast<double*>(wbase + SM::kRingOff);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(wbase + SM::kBarOff);
+    volatile int* progress = reinterpret_cast<volatile int*>(wbase + SM::kProgressOff);
+    double* out = UPPER ? a.vpoll : a.tmp;
+    const bool par = ILU0 && a.n_interior < a.n; // ghost rows exist (ParallelOverlappingILU0 leaves them alone)
+    const int q_lo = a.slices[s0].q0;
+    const int q_hi = a.slices[s1 - 1].q0 + a.slices[s1 - 1].count;
+    PROF_DECL;
 
-        auto slot0 = [&](const SliceMeta& m) { return UPPER ? m.base + m.wl + 1 : m.base; };
-        auto width = [&](const SliceMeta& m) { return UPPER ? m.wu : m.wl; };
-        auto in_ring = [&](int p, const SliceMeta& m) {
-            return UPPER ? (p >= m.q0 + m.count && p < m.q0 + m.count + kRingValid && p < q_hi)
-                         : (p < m.q0 && p >= m.q0 - kRingValid && p >= q_lo);
-        };
-        // request the staged part of slice t: block values and columns of its first kPrefetch slot
-        // rows, and its Dinv
-        auto request = [&](int t) {
-            if (t < ns && lane == 0 && !(a.debug & 8)) {
-                const SliceMeta m = metas[t % kMetaWin];
-                const int st = t % NS;
-                unsigned char* sb = stage0 + (size_t)st * SM::kStageBytes;
-                const int wst = min(width(m), kPrefetch);
-                const unsigned bytes = (unsigned)wst * (32 * BB * 8 + 128) + (NEED_DINV ? SM::kDinvBytes : 0);
-                if (bytes == 0) {
-                    mbar_expect_tx(bars + st, 0);
-                } else {
-                    mbar_expect_tx(bars + st, bytes);
-                    if (wst > 0) {
-                        tma_load_1d(sb, a.M + (size_t)slot0(m) * 32 * BB, (unsigned)wst * 32 * BB * 8, bars + st);
-                        tma_load_1d(sb + SM::kBlkBytes + SM::kDinvBytes, a.slot_col + (size_t)slot0(m) * 32,
-                                    (unsigned)wst * 128, bars + st);
-                    }
-                    if (NEED_DINV)
-                        tma_load_1d(sb + SM::kBlkBytes, a.dinv_s + (size_t)slice_id(t) * 32 * BB, SM::kDinvBytes, bars + st);
-                }
-            }
-        };
-        auto stage_cols = [&](int t) {
-            return reinterpret_cast<const int*>(stage0 + (size_t)(t % NS) * SM::kStageBytes + SM::kBlkBytes + SM::kDinvBytes);
-        };
-        // speculative loads for slice t (its stage must have landed): own input + external dependencies
-        auto load_ahead = [&](int t, int (&cj)[kPrefetch], double (&ext)[kPrefetch][B], double (&in)[B]) {
-            const SliceMeta m = metas[t % kMetaWin];
-            const int* cols = stage_cols(t);
-            const int q = m.q0 + lane;
+    // Everything about the step in stage `stg` that does not depend on the steps before it; no
+    // branches, so that it schedules into the running step's basic block.  Harmless on a stage
+    // that holds no step (zeros or an old record): it only issues loads.
+    auto look_ahead = [&](int stg, CwStep<B>& S) {
+        const unsigned char* sb = wbase + (size_t)stg * SM::kStageBytes;
+        S.hdr = *reinterpret_cast<const int4*>(sb + SM::kHdrOff);
+        const int* cols = reinterpret_cast<const int*>(sb + SM::kColOff);
 #pragma unroll
-            for (int s = 0; s < kPrefetch; ++s)
-                cj[s] = (lane < m.count && s < width(m)) ? cols[s * 32 + lane] : -1;
+        for (int s = 0; s < kPrefetch; ++s) {
+            const int c = cols[s * 32 + lane];
+            S.cj[s] = (s < (S.hdr.z & 0xffff)) ? c : -1;
+        }
 #pragma unroll
-            for (int s = 0; s < kPrefetch; ++s)
-                if (cj[s] >= 0 && !in_ring(cj[s], m) && !(a.debug & 4))
-                    rec_load_strong<B>(out, (size_t)cj[s], ext[s]);
-            if (a.debug & 4) {
+        for (int s = 0; s < kPrefetch; ++s) {
 #pragma unroll
-                for (int r = 0; r < B; ++r)
-                    in[r] = 1.0;
-            } else if (lane < m.count) {
-                if (UPPER) {
-                    rec_load_strong<B>(a.tmp, (size_t)q, in);
-                } else {
-                    const bool ghost = ILU0 && a.n_interior < a.n && a.r2n[q] >= a.n_interior;
+            for (int r = 0; r < B; ++r)
+                S.ext[s][r] = 0.0;
+            const bool e = cw_is_ext(S.cj[s]) && !CW_DBG(2);
+            rec_load_ahead_if<B>(e, out, e ? (size_t)S.cj[s] : (size_t)0, S.ext[s]);
+        }
+        const bool act = lane < S.hdr.y;
+        const size_t q = act ? (size_t)(S.hdr.x + lane) : (size_t)0; // idle lanes load row 0: harmless, never stored
+        if (UPPER) {
+            rec_load_weak<B>(a.tmp, q, S.in);
+        } else {
+#pragma unroll
+            for (int r = 0; r < B; ++r)
+                S.in[r] = __ldcs(a.d + VIDX(a.n, q, r));
+            if (par) { // multi-rank ILU0 only
+                if (a.r2n[q] >= a.n_interior) {
 #pragma unroll
                     for (int r = 0; r < B; ++r)
-                        in[r] = ghost ? (a.ghost_zero ? 0.0 : a.v[VIDX(a.n, q, r)]) : a.d[VIDX(a.n, q, r)];
+                        S.in[r] = a.ghost_zero ? 0.0 : a.v[VIDX(a.n, q, r)];
                 }
             }
-        };
-
-        for (int t = 0; t < NS - 1; ++t)
-            request(t);
-        int cjA[kPrefetch], cjB[kPrefetch];
-        double extA[kPrefetch][B], extB[kPrefetch][B], inA[B], inB[B];
-        bool haveA = false;
-        if (ns > 0) {
-            if (!(a.debug & 8))
-                mbar_wait(bars + 0, 0);
-            load_ahead(0, cjA, extA, inA);
-            haveA = true;
         }
+    };
 
-        for (int t = 0; t < ns; ++t) {
-            if (t > 0 && (t % (kMetaWin / 2)) == 0) {
-                __syncwarp();
-                fill_meta(t + kMetaWin / 2, kMetaWin / 2);
-                __syncwarp();
-            }
-#ifdef OPMB200_PROFILE
-            long long tprev__ = clock64();
-#endif
-            const int st = t % NS;
-            const unsigned parity = (unsigned)(t / NS) & 1u;
-            const SliceMeta m = metas[t % kMetaWin];
-            const bool active = lane < m.count;
-            const int q = m.q0 + lane;
-            const int w = width(m);
-            const int sr0 = slot0(m);
-            request(t + NS - 1); // its stage was released at the end of step t-1
-            PROF_MARK(0);
-            if (!haveA) {
-                if (!(a.debug & 8))
-                    mbar_wait(bars + st, parity);
-                load_ahead(t, cjA, extA, inA);
-            }
-            PROF_MARK(1);
-            const double* sblk = reinterpret_cast<const double*>(stage0 + (size_t)st * SM::kStageBytes);
-            const double* sdinv = reinterpret_cast<const double*>(stage0 + (size_t)st * SM::kStageBytes + SM::kBlkBytes);
+    int st0 = 0, st1 = 1 % NS, st2 = 2 % NS; // stages of steps t, t+1, t+2
+    unsigned ph1 = (1 / NS) & 1u, ph2 = (2 / NS) & 1u;
 
-            // look ahead one slice if its stage has already landed (it was requested NS-1 steps ago)
-            bool haveB = (t + 1 < ns) && ((a.debug & 8) || mbar_try_wait(bars + (t + 1) % NS, (unsigned)((t + 1) / NS) & 1u));
-            haveB = __all_sync(0xffffffffu, haveB);
-            if (haveB)
-                load_ahead(t + 1, cjB, extB, inB);
-            // far look-ahead: pull the stream of slice t+12 into the L2 (TMA covers the last hop only)
-            if (lane == 0 && t + 12 < ns) {
-                const SliceMeta mp = metas[(t + 12) % kMetaWin];
-                const int wp = min(width(mp), kPrefetch);
-                if (wp > 0) {
-                    l2_prefetch_bulk(a.M + (size_t)slot0(mp) * 32 * BB, (unsigned)wp * 32 * BB * 8);
-                    l2_prefetch_bulk(a.slot_col + (size_t)slot0(mp) * 32, (unsigned)wp * 128);
-                }
-                if (NEED_DINV)
-                    l2_prefetch_bulk(a.dinv_s + (size_t)slice_id(t + 12) * 32 * BB, SM::kDinvBytes);
-            }
-
-            PROF_MARK(2);
-            double rhs[B], yi[B], res[B];
-            bool ghost = false;
-            if (active) {
-                if (ILU0 && a.n_interior < a.n)
-                    ghost = a.r2n[q] >= a.n_interior;
+    // one step: S is the running step (looked ahead one step ago), N receives the look-ahead of the
+    // next one; ok1 tells whether stage st1 (step t+1) had landed when it was tested a step ago.
+    // Returns the same for step t+2.
+    auto step = [&](int t, bool ok1, CwStep<B>& S, CwStep<B>& N) -> bool {
+        PROF_MARK(5);
+        // ---- rarely taken branches first, then ONE basic block ---------------------------------
+        if (!ok1)
+            mbar_wait(full + st1, ph1);
+        PROF_MARK(0);
+        // the next step's samples travel while this step waits for its own (sampling only after the
+        // wait costs the lower sweep 40 % on C3 -- measured)
+        const bool ok2 = (t + 2 < ns) ? mbar_try_wait(full + st2, ph2) : true; // consumed one step from now
+        look_ahead(st1, N);
+        if (S.hdr.z & kCwHasExt) { // warp-uniform: the lead chunks of a wavefront never enter
+            unsigned pending = 0;
 #pragma unroll
-                for (int r = 0; r < B; ++r) {
-                    yi[r] = inA[r];
-                    rhs[r] = UPPER ? (ILU0 ? inA[r] : 0.0) : inA[r];
-                }
-                if (!UPPER)
-                    rec_store_sentinel<B>(a.vpoll, (size_t)q); // arm the upper sweep's records
-
-                // ---- dependencies: ring (same chunk, recent) or L2 (other chunks) -----------------------
-                double xv[kPrefetch][B];
-                unsigned pending = 0;
+            for (int s = 0; s < kPrefetch; ++s)
+                if (cw_is_ext(S.cj[s]) && !rec_valid<B>(S.ext[s]))
+                    pending |= 1u << s;
+            if (__any_sync(0xffffffffu, pending != 0) && !CW_DBG(2)) {
+                // dependencies outside the ring that had not arrived when they were sampled one step
+                // ago.  At chunk start the producers may be a long way off: poll slowly.
+                int tries = 0;
+                do {
+                    if (t == 0)
+                        __nanosleep(100);
+                    else if (++tries > 4)
+                        __nanosleep(20);
 #pragma unroll
-                for (int s = 0; s < kPrefetch; ++s)
-                    if (cjA[s] >= 0) {
-                        if (in_ring(cjA[s], m)) {
-#pragma unroll
-                            for (int r = 0; r < B; ++r)
-                                xv[s][r] = ring[r * kRing + (cjA[s] & (kRing - 1))];
-                        } else {
-#pragma unroll
-                            for (int r = 0; r < B; ++r)
-                                xv[s][r] = extA[s][r];
-                            if (!rec_valid<B>(xv[s]) && !(a.debug & 1))
-                                pending |= 1u << s;
+                    for (int s = 0; s < kPrefetch; ++s)
+                        if (pending & (1u << s)) {
+                            rec_load_strong<B>(out, (size_t)S.cj[s], S.ext[s]);
+                            if (rec_valid<B>(S.ext[s]))
+                                pending &= ~(1u << s);
                         }
-                    }
-                while (pending) {
+                } while (__any_sync(0xffffffffu, pending != 0));
+            }
+        }
+        PROF_MARK(t == 0 ? 7 : 2);
+        if (t == 0)
+            PROF_CHUNK(chunk, 1);
+        const int q = S.hdr.x + lane;
+        const bool active = lane < S.hdr.y;
+        double extra[B]; // rows wider than the staged window (NNC / well rows): the rest, from memory
 #pragma unroll
-                    for (int s = 0; s < kPrefetch; ++s)
-                        if (pending & (1u << s))
-                            rec_load_strong<B>(out, (size_t)cjA[s], xv[s]);
-#pragma unroll
-                    for (int s = 0; s < kPrefetch; ++s)
-                        if ((pending & (1u << s)) && rec_valid<B>(xv[s]))
-                            pending &= ~(1u << s);
-                }
-                PROF_MARK(3);
-#pragma unroll
-                for (int s = 0; s < kPrefetch; ++s)
-                    if (cjA[s] >= 0) {
-                        double blk[BB];
-#pragma unroll
-                        for (int e = 0; e < BB; ++e)
-                            blk[e] = sblk[(s * BB + e) * 32 + lane];
-                        if (UPPER && !ILU0)
-                            blk_umv<B>(blk, xv[s], rhs);
-                        else
-                            blk_mmv<B>(blk, xv[s], rhs);
-                    }
-                for (int s = kPrefetch; s < w; ++s) { // rows wider than the staged window: straight from memory
+        for (int r = 0; r < B; ++r)
+            extra[r] = 0.0;
+        if ((S.hdr.z & 0xffff) > kPrefetch) {
+            if (active) {
+                const int sr0 = S.hdr.w;
+                for (int s = kPrefetch; s < (S.hdr.z & 0xffff); ++s) {
                     const int cc = __ldg(a.slot_col + (size_t)(sr0 + s) * 32 + lane);
                     if (cc < 0)
                         continue;
@@ -1584,83 +1691,203 @@ __global__ void __launch_bounds__(kChunkWarps * 32, 1) chunk_sweep_kernel(ChunkS
 #pragma unroll
                     for (int e = 0; e < BB; ++e)
                         bl[e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
-                    if (in_ring(cc, m)) {
+                    const bool in_ring = UPPER ? (cc >= S.hdr.x + S.hdr.y && cc < S.hdr.x + S.hdr.y + kRingValid && cc < q_hi)
+                                               : (cc < S.hdr.x && cc >= S.hdr.x - kRingValid && cc >= q_lo);
+                    if (in_ring) {
 #pragma unroll
                         for (int r = 0; r < B; ++r)
                             xs[r] = ring[r * kRing + (cc & (kRing - 1))];
                     } else {
                         do {
                             rec_load_strong<B>(out, (size_t)cc, xs);
-                        } while (!rec_valid<B>(xs) && !(a.debug & 1));
+                        } while (!rec_valid<B>(xs));
                     }
-                    if (UPPER && !ILU0)
-                        blk_umv<B>(bl, xs, rhs);
-                    else
-                        blk_mmv<B>(bl, xs, rhs);
+                    blk_umv<B>(bl, xs, extra);
                 }
+            }
+            __syncwarp();
+        }
 
-                // ---- finish the rows --------------------------------------------------------------------------
-                double di[BB];
-                if (NEED_DINV) {
+        // ---- the step proper: one basic block ---------------------------------------------------
+        PROF_MARK(1);
+        const unsigned char* sb = wbase + (size_t)st0 * SM::kStageBytes;
+        double rhs[B], yi[B], res[B];
 #pragma unroll
-                    for (int e = 0; e < BB; ++e)
-                        di[e] = sdinv[e * 32 + lane];
-                }
-                if (!UPPER) {
-                    if (ILU0) {
+        for (int r = 0; r < B; ++r) {
+            yi[r] = S.in[r];
+            rhs[r] = (UPPER && !ILU0) ? 0.0 : S.in[r];
+        }
+        if (!UPPER && !CW_DBG(1))
+            rec_store_sentinel_if<B>(active, a.vpoll, (size_t)(active ? q : 0)); // arm the upper sweep's records
+        // accumulate in slot order (the reference's summation order).  Straight-line code, no test
+        // of the width: a slot without a dependency has x = 0, and the stage rows beyond the width
+        // hold zeros (cw_stream_fill_kernel), so it adds exactly nothing.  All shared-memory loads
+        // of the step issue back to back ahead of the one dependent DFMA chain.
+        double di[BB];
+        if (NEED_DINV)
+            cw_load_slot<BB>(sb + SM::kDinvOff, lane, di);
 #pragma unroll
-                        for (int r = 0; r < B; ++r)
-                            res[r] = rhs[r];
-                    } else {
-                        blk_mv<B>(di, rhs, res);
-                    }
-                } else if (ILU0) {
-                    if (ghost) {
+        for (int s = 0; s < kPrefetch; ++s) {
+            double x[B], blk[BB];
 #pragma unroll
-                        for (int r = 0; r < B; ++r)
-                            res[r] = rhs[r];
-                    } else {
-                        blk_mv<B>(di, rhs, res);
-                    }
-                } else {
-                    blk_mmv<B>(di, rhs, yi);
-#pragma unroll
-                    for (int r = 0; r < B; ++r)
-                        res[r] = yi[r];
-                }
+            for (int r = 0; r < B; ++r)
+                x[r] = S.ext[s][r];
+            if (cw_is_ring(S.cj[s]) && !CW_DBG(4)) { // predicated loads, no branch
 #pragma unroll
                 for (int r = 0; r < B; ++r)
-                    res[r] = guard(res[r]);
+                    x[r] = ring[r * kRing + (S.cj[s] & (kRing - 1))];
             }
-            PROF_MARK(4);
-            __syncwarp(); // every lane has finished reading the ring and this stage
-            PROF_MARK(5);
-            if (active) {
+            cw_load_slot<BB>(sb + SM::kBlkOff + s * SM::kSlotBytes, lane, blk);
+            if (CW_DBG(64)) {
+            } else if (UPPER && !ILU0)
+                blk_umv<B>(blk, x, rhs);
+            else
+                blk_mmv<B>(blk, x, rhs);
+        }
 #pragma unroll
-                for (int r = 0; r < B; ++r) {
-                    ring[r * kRing + (q & (kRing - 1))] = res[r];
-                    if (UPPER)
+        for (int r = 0; r < B; ++r)
+            rhs[r] = (UPPER && !ILU0) ? rhs[r] + extra[r] : rhs[r] - extra[r];
+        if (NEED_DINV) {
+            if (!UPPER) {
+                blk_mv<B>(di, rhs, res); // DILU: y_i = Dinv_i (d_i - sum)
+            } else if (ILU0) {
+                blk_mv<B>(di, rhs, res); // v_i = Dinv_i (y_i - sum)
+                if (par) {
+                    if (active && a.r2n[q] >= a.n_interior) { // ghost rows keep y_i
+#pragma unroll
+                        for (int r = 0; r < B; ++r)
+                            res[r] = rhs[r];
+                    }
+                }
+            } else {
+                blk_mmv<B>(di, rhs, yi); // v_i = y_i - Dinv_i sum
+#pragma unroll
+                for (int r = 0; r < B; ++r)
+                    res[r] = yi[r];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < B; ++r)
+                res[r] = rhs[r]; // ILU0 lower: L_ii = I
+        }
+#pragma unroll
+        for (int r = 0; r < B; ++r)
+            res[r] = guard(res[r]);
+        if (active && !CW_DBG(4)) {
+#pragma unroll
+            for (int r = 0; r < B; ++r)
+                ring[r * kRing + (q & (kRing - 1))] = res[r];
+        }
+        if (!CW_DBG(1)) {
+            rec_store_strong_if<B>(active, out, (size_t)(active ? q : 0), res);
+            if (UPPER) {
+                if (active) {
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
                         a.v[VIDX(a.n, q, r)] = res[r];
                 }
-                rec_store_strong<B>(out, (size_t)q, res);
-                if (UPPER)
-                    rec_store_sentinel<B>(a.tmp, (size_t)q);
+                rec_store_sentinel_if<B>(active, a.tmp, (size_t)(active ? q : 0)); // re-arm for the next apply
             }
-            __syncwarp(); // ring writes visible to the whole warp before the next slice
-            PROF_MARK(6);
-            haveA = haveB;
-            if (haveB) {
+        }
+        PROF_MARK(3);
+        __syncwarp(); // ring writes visible to the warp; every lane is done with this stage
+        if (lane == 0)
+            *progress = t + 1; // releases the stage to the loader
+        PROF_MARK(4);
+        st0 = st1;
+        st1 = st2;
+        ph1 = ph2;
+        if (++st2 == NS) {
+            st2 = 0;
+            ph2 ^= 1u;
+        }
+        return ok2;
+    };
+
+    CwStep<B> SA, SB;
+    PROF_CHUNK(chunk, 0);
+    mbar_wait(full + 0, 0u);
+    look_ahead(0, SA);
+    bool ok1 = ns > 1 ? mbar_try_wait(full + st1, ph1) : true;
+    PROF_MARK(6);
+    for (int t = 0; t < ns; t += 2) {
+        ok1 = step(t, ok1, SA, SB);
+        if (t + 1 < ns)
+            ok1 = step(t + 1, ok1, SB, SA);
+    }
+    PROF_CHUNK(chunk, 2);
+    PROF_FLUSH(ns);
+}
+
+// fills the value part of the step records after a factorisation: block values from the SELL
+// slots (A for DILU, F for ILU0), Dinv from its slice layout.  One warp per slice and direction.
+template <int B>
+__global__ void __launch_bounds__(256) cw_stream_fill_kernel(int nslices, const SliceMeta* __restrict__ slices,
+                                                             const double* __restrict__ M, const double* __restrict__ dinv_s,
+                                                             unsigned char* __restrict__ lower, unsigned char* __restrict__ upper,
+                                                             int lower_has_dinv)
+{
+    using SM = CwSmem<B>;
+    constexpr int BB = B * B;
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+    const int nw = (int)((gridDim.x * (size_t)blockDim.x) >> 5);
+    for (int job = gw; job < 2 * nslices; job += nw) {
+        const int s = job >> 1;
+        const bool up = job & 1;
+        const SliceMeta m = slices[s];
+        const int w = min(up ? m.wu : m.wl, kPrefetch);
+        const int sr0 = up ? m.base + m.wl + 1 : m.base;
+        const bool with_dinv = up || lower_has_dinv;
+        const size_t rec = (size_t)cw_record_bytes<B>(with_dinv);
+        unsigned char* dst = up ? upper + (size_t)(nslices - 1 - s) * rec : lower + (size_t)s * rec;
+        for (int k = 0; k < kPrefetch; ++k) {
+            double* slot = reinterpret_cast<double*>(dst + SM::kBlkOff + k * SM::kSlotBytes) + lane;
 #pragma unroll
-                for (int s = 0; s < kPrefetch; ++s) {
-                    cjA[s] = cjB[s];
+            for (int e = 0; e < BB; ++e)
+                slot[e * 32] = k < w ? __ldcs(M + elem_index<BB>(sr0 + k, lane, e)) : 0.0;
+        }
+        if (with_dinv) {
+            double* slot = reinterpret_cast<double*>(dst + SM::kDinvOff) + lane;
 #pragma unroll
-                    for (int r = 0; r < B; ++r)
-                        extA[s][r] = extB[s][r];
-                }
-#pragma unroll
-                for (int r = 0; r < B; ++r)
-                    inA[r] = inB[r];
-            }
+            for (int e = 0; e < BB; ++e)
+                slot[e * 32] = __ldcs(dinv_s + (size_t)s * 32 * BB + e * 32 + lane);
+        }
+    }
+}
+
+template <int B, bool ILU0, bool UPPER>
+__global__ void __launch_bounds__(kCwWarps * 64, 1) cw_sweep_kernel(CwArgs a)
+{
+    using SM = CwSmem<B>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned int ticket = take_ticket(a.ticket);
+    const bool skip = a.check_done && a.sc->done;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wi = (warp + ((warp >= kCwWarps && CW_DBG(32)) ? 1 : 0)) % kCwWarps; // compute warp wi and loader warp wi + kCwWarps share a chunk
+    unsigned char* wbase = smem_raw + (size_t)wi * SM::kWarpBytes;
+    // zero-filled stages: see the slot loop of cw_compute
+    for (int i = threadIdx.x; i < SM::kCtaBytes / 16; i += blockDim.x)
+        reinterpret_cast<int4*>(smem_raw)[i] = make_int4(0, 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes before the TMA writes
+    __syncthreads();
+    if (warp < kCwWarps && lane == 0) {
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbase + SM::kBarOff);
+        for (int i = 0; i < SM::kStages; ++i)
+            mbar_init(bars + i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int cf = (int)ticket * kCwWarps + wi;
+    if (!skip && cf < a.nchunks) {
+        const int c = UPPER ? a.nchunks - 1 - cf : cf;
+        const int s0 = a.chunk_slice0[c], s1 = a.chunk_slice0[c + 1];
+        if (s1 > s0) {
+            if (warp >= kCwWarps) {
+                if (lane == 0)
+                    cw_loader<B, ILU0, UPPER>(a, wbase, s0, s1);
+            } else
+                cw_compute<B, ILU0, UPPER>(a, wbase, s0, s1, lane, c);
         }
     }
     return_ticket(a.ticket);
@@ -1854,3 +2081,4 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(HaloDev h, int64_t n, co
 }
 
 } // namespace opmb200
+

@@ -62,6 +62,9 @@ struct Layout {
 
     std::vector<int32_t> slot_col; // [n_slot_rows*32]
     std::vector<int32_t> slot_src; // [n_slot_rows*32]
+    // mode 1: slot_col with bit 30 set where the dependency is served by the chunk's shared-memory
+    // ring (same chunk, at most kRingValid positions back / ahead), see cw_sweep_kernel
+    std::vector<int32_t> sweep_col; // [n_slot_rows*32]
     // DILU: for every L slot (compact L numbering) the slot of the transposed block, or -1
     std::vector<int32_t> l_transpose; // [n_l_slot_rows*32]
     // ILU0: per compact L slot, the (source slot in row j, destination slot in row i) update pairs

@@ -120,8 +120,8 @@ struct opmb200_solver {
     int throttle = 3;
     int schedule = 0;   // 0 levels, 1 chunks
     int chunk_rows = 0; // <= 0: automatic
-    int prefetch = 12;  // L2 prefetch distance of the chunk sweeps, in slices
-    int debug = 0;      // timing experiments (results are wrong when != 0)
+    int prefetch = 0;   // L2 look-ahead of the chunk sweeps' loader warps, in steps
+    int debug = 0;      // OPMB200_PROFILE builds: timing experiments (wrong results)
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -132,6 +132,7 @@ struct opmb200_solver {
     DevBuf<SliceMeta> slices;
     DevBuf<int> slot_col, slot_src, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag, chunk_slice0;
     DevBuf<double> A, F, dinv, dinv_s, dinv_rec, vals_native;
+    DevBuf<unsigned char> stream_lo, stream_up; // chunk schedule: step records of the lower / upper sweep
     DevBuf<double> vx, vr, vp, vv, vt, vy, vrt, vw, nat0, nat1;
     DevBuf<double> vtmp, vpoll; // dependency records of the sweeps, [n][2 or 4]
     DevBuf<double> partials, hist, sums, dot_out;
@@ -350,13 +351,14 @@ SweepArgs sweep_args(opmb200_solver* s, const double* d, double* v, int ghost_ze
 int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
 {
     if (s->schedule == 1) { // chunked wavefronts: one warp per chunk
-        ChunkSweepArgs c;
+        CwArgs c;
         c.nchunks = s->L.n_chunks;
         c.chunk_slice0 = s->chunk_slice0.p;
         c.slices = a.slices;
         c.slot_col = a.slot_col;
+        c.stream = upper ? s->stream_up.p : s->stream_lo.p;
+        c.nslices = s->L.n_slices;
         c.M = a.M;
-        c.dinv_s = s->dinv_s.p;
         c.d = a.d;
         c.tmp = a.tmp;
         c.vpoll = a.vpoll;
@@ -365,19 +367,20 @@ int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
         c.n = a.n;
         c.n_interior = a.n_interior;
         c.ghost_zero = a.ghost_zero;
+        c.prefetch = s->prefetch;
         c.debug = s->debug;
         c.ticket = a.ticket;
         c.sc = a.sc;
         c.check_done = a.check_done;
-        const int cgrid = std::max(1, (s->L.n_chunks + kChunkWarps - 1) / kChunkWarps);
+        const int cgrid = std::max(1, (s->L.n_chunks + kCwWarps - 1) / kCwWarps);
         DISPATCH_B(s->b, {
-            constexpr int smem = ChunkSmem<B>::kCtaBytes;
+            constexpr int smem = CwSmem<B>::kCtaBytes;
             if (s->prec == PREC_ILU0) {
-                if (upper) chunk_sweep_kernel<B, true, true><<<cgrid, kChunkWarps * 32, smem, s->stream>>>(c);
-                else chunk_sweep_kernel<B, true, false><<<cgrid, kChunkWarps * 32, smem, s->stream>>>(c);
+                if (upper) cw_sweep_kernel<B, true, true><<<cgrid, kCwWarps * 64, smem, s->stream>>>(c);
+                else cw_sweep_kernel<B, true, false><<<cgrid, kCwWarps * 64, smem, s->stream>>>(c);
             } else {
-                if (upper) chunk_sweep_kernel<B, false, true><<<cgrid, kChunkWarps * 32, smem, s->stream>>>(c);
-                else chunk_sweep_kernel<B, false, false><<<cgrid, kChunkWarps * 32, smem, s->stream>>>(c);
+                if (upper) cw_sweep_kernel<B, false, true><<<cgrid, kCwWarps * 64, smem, s->stream>>>(c);
+                else cw_sweep_kernel<B, false, false><<<cgrid, kCwWarps * 64, smem, s->stream>>>(c);
             }
         });
         return check_launch(s, upper ? "upper chunk sweep" : "lower chunk sweep");
@@ -444,7 +447,15 @@ int prec_update(opmb200_solver* s)
         if (s->prec == PREC_ILU0) ilu0_factor_kernel<B><<<grid, kCtaThreads, 0, s->stream>>>(a);
         else dilu_factor_kernel<B><<<grid, kCtaThreads, 0, s->stream>>>(a);
     });
-    return check_launch(s, "factorisation");
+    TRY(check_launch(s, "factorisation"));
+    if (s->schedule == 1 && s->L.n_slices > 0) { // chunk sweeps read step records, not the SELL slots
+        const int fgrid = std::max(1, std::min(s->num_sms * 8, (2 * s->L.n_slices + 7) / 8));
+        DISPATCH_B(s->b, (cw_stream_fill_kernel<B><<<fgrid, 256, 0, s->stream>>>(
+                          s->L.n_slices, s->slices.p, s->prec == PREC_ILU0 ? s->F.p : s->A.p, s->dinv_s.p, s->stream_lo.p,
+                          s->stream_up.p, s->prec == PREC_DILU ? 1 : 0)));
+        TRY(check_launch(s, "stream fill"));
+    }
+    return OPMB200_SUCCESS;
 }
 
 int relayout(opmb200_solver* s, const double* dev_vals)
@@ -524,7 +535,7 @@ int parse_options(opmb200_solver* s, const char* json)
             return fail(OPMB200_BAD_OPTIONS, "b200.schedule must be \"levels\" or \"chunks\"");
         s->schedule = sched == "chunks" ? 1 : 0;
         s->chunk_rows = prm.get<int>("b200.chunk_rows", 0);
-        s->prefetch = std::max(1, std::min(24, prm.get<int>("b200.prefetch_slices", 12)));
+        s->prefetch = std::max(0, std::min(32, prm.get<int>("b200.prefetch_slices", 0)));
         s->debug = prm.get<int>("b200.debug_timing", 0);
     } catch (const std::exception& e) {
         return fail(OPMB200_BAD_OPTIONS, e.what());
@@ -706,6 +717,33 @@ int opmb200_row_coloring(int64_t n, const int32_t* rowptr, const int32_t* colidx
     return OPMB200_SUCCESS;
 }
 
+int opmb200_plan_schedule(int block_size, int64_t n_rows, int64_t nnzb, const int32_t* rowptr, const int32_t* colidx,
+                          int64_t n_interior, int schedule, int chunk_rows, int32_t* n_slices, int32_t* n_chunks,
+                          int32_t* chunk_rows_out, double* est_steps, int32_t* position_to_row, int32_t* slice_first,
+                          int32_t* chunk_first_slice)
+{
+    Layout L;
+    std::string err;
+    const int rc = build_layout(block_size, n_rows, nnzb, rowptr, colidx, n_interior, false, schedule, chunk_rows, L, err);
+    if (rc != OPMB200_SUCCESS)
+        return fail(rc, err);
+    if (n_slices)
+        *n_slices = L.n_slices;
+    if (n_chunks)
+        *n_chunks = L.n_chunks;
+    if (chunk_rows_out)
+        *chunk_rows_out = L.chunk_rows;
+    if (est_steps)
+        *est_steps = L.est_steps;
+    if (position_to_row)
+        std::copy(L.r2n.begin(), L.r2n.end(), position_to_row);
+    if (slice_first)
+        std::copy(L.slice_q0.begin(), L.slice_q0.begin() + L.n_slices + 1, slice_first);
+    if (chunk_first_slice && schedule == 1)
+        std::copy(L.chunk_slice0.begin(), L.chunk_slice0.end(), chunk_first_slice);
+    return OPMB200_SUCCESS;
+}
+
 int opmb200_partition_simple(int32_t num_cells, int32_t num_domains, int32_t* part)
 {
     if (!part || num_cells < 0 || num_domains <= 0)
@@ -814,6 +852,50 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
                              L.slice_wu[i], L.slice_level[i], L.slice_lrank[i], 0};
     CUDA_TRY(s->slices.upload(meta, st));
     CUDA_TRY(s->slot_col.upload(L.slot_col, st));
+    std::vector<int32_t> rec_lo, rec_up; // header + column positions of every step record (host staging)
+    if (s->schedule == 1 && s->prec != PREC_NONE && L.n_slices > 0) {
+        size_t rec_bytes_lo = 0, rec_bytes_up = 0;
+        DISPATCH_B(block_size, {
+            rec_bytes_lo = (size_t)cw_record_bytes<B>(s->prec == PREC_DILU);
+            rec_bytes_up = (size_t)cw_record_bytes<B>(true);
+        });
+        CUDA_TRY(s->stream_lo.alloc(rec_bytes_lo * L.n_slices));
+        CUDA_TRY(s->stream_up.alloc(rec_bytes_up * L.n_slices));
+        constexpr int kStatic = 128; // ints: 32 header + kPrefetch*32 columns (CwSmem::kBlkOff bytes)
+        rec_lo.assign((size_t)L.n_slices * kStatic, -1);
+        rec_up.assign((size_t)L.n_slices * kStatic, -1);
+        for (int i = 0; i < L.n_slices; ++i) {
+            const int q0 = L.slice_q0[i], cnt = L.slice_q0[i + 1] - L.slice_q0[i];
+            const int wl = L.slice_wl[i], wu = L.slice_wu[i], base = L.slice_base[i];
+            int32_t* lo = rec_lo.data() + (size_t)i * kStatic;
+            int32_t* up = rec_up.data() + (size_t)(L.n_slices - 1 - i) * kStatic;
+            lo[0] = q0, lo[1] = cnt, lo[2] = wl, lo[3] = base;
+            up[0] = q0, up[1] = cnt, up[2] = wu, up[3] = base + wl + 1;
+            auto is_ext = [](int32_t c) { return c >= 0 && !(c & kRingFlag); };
+            bool ext_lo = wl > kPrefetch, ext_up = wu > kPrefetch; // wide rows resolve their own dependencies
+            for (int k = 0; k < kPrefetch; ++k)
+                for (int lane = 0; lane < kSlice; ++lane) {
+                    if (k < wl) {
+                        const int32_t c = L.sweep_col[((size_t)base + k) * kSlice + lane];
+                        lo[32 + k * 32 + lane] = c;
+                        ext_lo = ext_lo || is_ext(c);
+                    }
+                    if (k < wu) {
+                        const int32_t c = L.sweep_col[((size_t)base + wl + 1 + k) * kSlice + lane];
+                        up[32 + k * 32 + lane] = c;
+                        ext_up = ext_up || is_ext(c);
+                    }
+                }
+            if (ext_lo)
+                lo[2] |= kCwHasExt;
+            if (ext_up)
+                up[2] |= kCwHasExt;
+        }
+        CUDA_TRY(cudaMemcpy2DAsync(s->stream_lo.p, rec_bytes_lo, rec_lo.data(), kStatic * 4, kStatic * 4, L.n_slices,
+                                   cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpy2DAsync(s->stream_up.p, rec_bytes_up, rec_up.data(), kStatic * 4, kStatic * 4, L.n_slices,
+                                   cudaMemcpyHostToDevice, st));
+    }
     CUDA_TRY(s->slot_src.upload(L.slot_src, st));
     CUDA_TRY(s->r2n.upload(L.r2n, st));
     CUDA_TRY(s->n2r.upload(L.n2r, st));
@@ -895,11 +977,11 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
     }
     if (s->schedule == 1) {
         DISPATCH_B(block_size, {
-            constexpr int smem = ChunkSmem<B>::kCtaBytes;
-            CUDA_TRY(cudaFuncSetAttribute(chunk_sweep_kernel<B, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CUDA_TRY(cudaFuncSetAttribute(chunk_sweep_kernel<B, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CUDA_TRY(cudaFuncSetAttribute(chunk_sweep_kernel<B, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CUDA_TRY(cudaFuncSetAttribute(chunk_sweep_kernel<B, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            constexpr int smem = CwSmem<B>::kCtaBytes;
+            CUDA_TRY(cudaFuncSetAttribute(cw_sweep_kernel<B, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CUDA_TRY(cudaFuncSetAttribute(cw_sweep_kernel<B, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CUDA_TRY(cudaFuncSetAttribute(cw_sweep_kernel<B, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+            CUDA_TRY(cudaFuncSetAttribute(cw_sweep_kernel<B, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         });
     }
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1213,8 +1295,9 @@ int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, doubl
     return OPMB200_SUCCESS;
 }
 
+
 #ifdef OPMB200_PROFILE
-int opmb200_prof_read(unsigned long long* out16, int reset)
+extern "C" int opmb200_prof_read(unsigned long long* out16, int reset)
 {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16);
@@ -1222,6 +1305,15 @@ int opmb200_prof_read(unsigned long long* out16, int reset)
         unsigned long long z[16] = {0};
         cudaMemcpyToSymbol(g_prof, z, sizeof z);
     }
+    return 0;
+}
+#endif
+
+#ifdef OPMB200_PROFILE
+extern "C" int opmb200_prof_chunks(unsigned long long* out, int nchunks)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_chunk_t, sizeof(unsigned long long) * 3 * (size_t)std::min(nchunks, 4096));
     return 0;
 }
 #endif

@@ -1,22 +1,27 @@
-import os, sys, ctypes as C
+"""In-kernel phase profile of the chunk sweeps (build with OPMB200_PROFILE=1):
+   OPMB200_PROFILE=1 python opm_simulators_b200/build.py && python scripts/prof_chunk.py [cfg] [scale] [prec] [prefetch]"""
+import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from opm_simulators_b200 import generators, _lib
 from opm_simulators_b200.flexible_solver import FlexibleSolver, MatrixAdapter
-scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-dbg = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-s = generators.config("C3", scale=scale); A = s["A"]
-fs = FlexibleSolver(MatrixAdapter(A), {"preconditioner": {"type": "dilu"}, "b200": {"schedule": "chunks", "debug_timing": dbg}})
-info = fs.info(); L = _lib.lib()
-out = (C.c_ulonglong * 16)()
-for what in (4, 5):
-    L.opmb200_prof_read(out, 1)
-    ms, nb = fs.time_kernel(what, 2, 10)
-    L.opmb200_prof_read(out, 1)
-    steps = info["n_slices"] * 12 * 2   # both sweeps run in each of 12 reps
-    print("kernel", what, "ms %.3f" % ms, "slices", info["n_slices"], "est_steps", info["est_steps"])
-    names = ["request", "wait stage", "look-ahead", "deps+poll", "accumulate+finish", "syncwarp1", "publish+syncwarp2"]
-    tot = sum(out[i] for i in range(7))
-    for i, nme in enumerate(names):
-        print("   %-20s %8.1f cycles/step  %5.1f%%" % (nme, out[i] / steps, 100.0 * out[i] / max(tot, 1)))
-    print("   total %.1f cycles/step" % (tot / steps))
+cfg = sys.argv[1] if len(sys.argv) > 1 else "C3"
+scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
+prec = sys.argv[3] if len(sys.argv) > 3 else "dilu"
+pf = int(sys.argv[4]) if len(sys.argv) > 4 else 16
+dims = [int(v) for v in sys.argv[5].split("x")] if len(sys.argv) > 5 else None
+s = generators.config(cfg, nx=dims[0], ny=dims[1], nz=dims[2]) if dims else generators.config(cfg, scale=scale); A = s["A"]
+fs = FlexibleSolver(MatrixAdapter(A), {"preconditioner": {"type": prec}, "b200": {"schedule": "chunks", "prefetch_slices": pf}})
+lib = _lib.lib()
+out = (ctypes.c_ulonglong * 16)()
+names = ["wait full", "look-ahead issue", "ext validate/poll", "compute+stores", "syncwarp+arrive", "loop overhead", "prologue", "wait for chunk start"]
+for what, name in ((4, "lower"), (5, "upper")):
+    lib.opmb200_prof_read(out, 1)
+    ms, nb = fs.time_kernel(what, 0, 10)
+    lib.opmb200_prof_read(out, 1)
+    steps, warps = out[8], out[9]
+    print(f"{name}: {ms:.3f} ms/launch, {steps} steps over {warps} chunk-walks; cycles per step:")
+    for i in range(8):
+        print(f"   {names[i]:20s} {out[i] / max(steps, 1):9.1f}")
+    print(f"   {'total':20s} {sum(out[i] for i in range(8)) / max(steps, 1):9.1f}")
+fs.close()

@@ -12,6 +12,7 @@ cfg = sys.argv[1] if len(sys.argv) > 1 else "C3"
 prec = sys.argv[2] if len(sys.argv) > 2 else "dilu"
 s = generators.config(cfg)
 A = s["A"]
-fs = FlexibleSolver(MatrixAdapter(A), {"tol": 1e-2, "maxiter": 200, "preconditioner": {"type": prec}})
+sched = sys.argv[3] if len(sys.argv) > 3 else "levels"
+fs = FlexibleSolver(MatrixAdapter(A), {"tol": 1e-2, "maxiter": 200, "preconditioner": {"type": prec}, "b200": {"schedule": sched}})
 x, r = np.zeros(A.n * A.b), s["rhs2"].copy()
 print(fs.apply(x, r), fs.info()["kernel_launches"])

@@ -335,3 +335,38 @@ def test_wide_rows_beyond_the_register_window():
         res = fs.apply(x, r)
         xo, ro, _ = orc.solve_serial(A.rowptr, A.col, A.val, d, prec=prec, tol=1e-9)
         assert abs(res.iterations - ro["iterations"]) <= 1 and rel_err(x, xo) < 1e-6
+
+
+@pytest.mark.parametrize("b,prec", [(3, "dilu"), (3, "ilu0"), (4, "dilu"), (2, "ilu0")])
+def test_tile_chunks_equal_the_level_schedule_bit_for_bit(b, prec, schedule):
+    """box grid cut into 8x4 tiles of grid lines (the shape the planner picks for C3): on a 7-point pattern
+    every row has at most 3 lower / 3 upper blocks, all schedules add them in the reference's order, so the
+    preconditioner apply of the chunk sweeps must equal the level sweeps' bit for bit -- and the oracle to 1e-10"""
+    if schedule != "chunks":
+        pytest.skip("compares the two schedules itself")
+    s = generators.blackoil_system(24, 40, 12, b=b, seed=21)
+    A = s["A"]
+    d = s["rhs2"]
+    out = {}
+    for name, b200 in (("levels", {"schedule": "levels"}), ("tiles", {"schedule": "chunks", "chunk_rows": -804}),
+                       ("strips", {"schedule": "chunks", "chunk_rows": -1602})):
+        fs = FlexibleSolver(MatrixAdapter(A), {"solver": "bicgstab", "tol": 1e-6, "maxiter": 100,
+                                              "preconditioner": {"type": prec}, "b200": b200})
+        if name != "levels":
+            assert fs.info()["chunk_rows"] == b200["chunk_rows"] and fs.info()["n_chunks"] > 4
+        v = np.zeros_like(d)
+        fs.preconditioner().apply(v, d)
+        x, r = np.zeros_like(d), d.copy()
+        res = fs.apply(x, r)
+        out[name] = (v, x, res.iterations)
+        fs.close()
+    if prec == "dilu":
+        vo = orc.dilu_apply(A.rowptr, A.col, A.val, orc.dilu_update(A.rowptr, A.col, A.val), d)
+    else:
+        vo = orc.ilu0_apply(A.rowptr, A.col, orc.ilu0_decompose(A.rowptr, A.col, A.val), d)
+    assert rel_err(out["levels"][0], vo) < TOL
+    for name in ("tiles", "strips"):
+        assert np.array_equal(out[name][0], out["levels"][0])
+        # the solve differs in the last bits only (the dot products add the rows in schedule order)
+        assert abs(out[name][2] - out["levels"][2]) <= 1
+        assert rel_err(out[name][1], out["levels"][1]) < 1e-6

@@ -229,3 +229,62 @@ def test_matrixmarket_roundtrip_and_block_reinterpretation(golden, tmp_path):
     matrixmarket.export_system(str(tmp_path / "sys"), A3, v)
     A4, r4 = matrixmarket.import_system(str(tmp_path / "sys"), 3)
     assert np.array_equal(A4.val, A3.val) and np.array_equal(r4, v)
+
+
+# ---- sweep schedules (host-only planner, opmb200_plan_schedule) -------------------------------------
+def _plan(A, schedule, chunk_rows=0, n_interior=None):
+    import ctypes as C
+    n = A.n
+    ns, nc, cr, est = C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+    r2n = np.zeros(n, np.int32)
+    sf = np.zeros(n + 1, np.int32)
+    cf = np.zeros(n + 2, np.int32)
+    _lib.check(_lib.lib().opmb200_plan_schedule(A.b, n, A.nnzb, A.rowptr, A.col, n if n_interior is None else n_interior,
+                                                schedule, chunk_rows, C.byref(ns), C.byref(nc), C.byref(cr), C.byref(est),
+                                                r2n.ctypes.data, sf.ctypes.data, cf.ctypes.data))
+    return dict(n_slices=ns.value, n_chunks=nc.value, chunk_rows=cr.value, est=est.value, r2n=r2n,
+                slice_first=sf[:ns.value + 1], chunk_first=cf[:nc.value + 1])
+
+
+def _check_schedule(A, P, chunks):
+    n = A.n
+    assert sorted(P["r2n"].tolist()) == list(range(n))
+    pos = np.empty(n, np.int64)
+    pos[P["r2n"]] = np.arange(n)
+    sl = np.searchsorted(P["slice_first"], pos, side="right") - 1          # slice of every row
+    assert (np.diff(P["slice_first"]) <= 32).all() and (np.diff(P["slice_first"]) > 0).all()
+    rows = np.repeat(np.arange(n), np.diff(A.rowptr))
+    lo = A.col < rows
+    # a row depends only on rows of earlier slices (lower sweep; the upper sweep is the mirror image)
+    assert (sl[A.col[lo]] < sl[rows[lo]]).all()
+    if chunks:
+        ch = np.searchsorted(P["chunk_first"], sl, side="right") - 1
+        assert (ch[A.col[lo]] <= ch[rows[lo]]).all()                       # in-order chunk start cannot deadlock
+        hi = A.col > rows
+        assert (ch[A.col[hi]] >= ch[rows[hi]]).all()
+
+
+@pytest.mark.parametrize("dims", [(12, 20, 9), (7, 33, 5), (16, 8, 1), (5, 1, 1)])
+def test_chunk_schedule_box_grids_use_line_tiles(dims):
+    s = generators.blackoil_system(*dims, b=2, seed=5, with_rhs=False)
+    A = s["A"]
+    for sched, cr in ((0, 0), (1, 0), (1, 64)):
+        P = _plan(A, sched, cr)
+        _check_schedule(A, P, sched == 1)
+
+
+def test_chunk_schedule_tiles_on_a_box_grid():
+    A = generators.blackoil_system(60, 64, 16, b=1, seed=5, with_rhs=False)["A"]
+    P = _plan(A, 1, 0)
+    assert P["chunk_rows"] < 0, "a clean box grid is cut into tiles of 32 grid lines"
+    _check_schedule(A, P, True)
+    # fewer, fuller steps than contiguous chunks of 32 lines
+    assert P["n_slices"] < _plan(A, 1, 32 * 60)["n_slices"]
+
+
+def test_chunk_schedule_falls_back_when_tiles_would_deadlock():
+    # non-neighbour connections pointing against the tile order make the tile numbering invalid
+    s = generators.blackoil_system(10, 24, 8, b=1, seed=6, nnc=40, with_rhs=False)
+    A = s["A"]
+    P = _plan(A, 1, 0)
+    _check_schedule(A, P, True)
