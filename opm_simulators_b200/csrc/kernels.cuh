@@ -1460,6 +1460,11 @@ __device__ __forceinline__ unsigned long long gtime()
         pacc__[i] += (unsigned long long)(now__ - tprev__);                                                            \
         tprev__ = now__;                                                                                               \
     } while (0)
+#define PROF_COUNT(i)                                                                                                  \
+    do {                                                                                                               \
+        if (lane == 0)                                                                                                 \
+            atomicAdd(&g_prof[i], 1ull);                                                                               \
+    } while (0)
 #define PROF_FLUSH(nsteps)                                                                                             \
     do {                                                                                                               \
         if (lane == 0) {                                                                                               \
@@ -1472,6 +1477,7 @@ __device__ __forceinline__ unsigned long long gtime()
 #else
 #define PROF_CHUNK(c, k)
 #define PROF_DECL
+#define PROF_COUNT(i)
 #define PROF_MARK(i)
 #define PROF_FLUSH(nsteps)
 #endif
@@ -1643,9 +1649,14 @@ __device__ __forceinline__ void cw_compute(const CwArgs& a, unsigned char* wbase
             mbar_wait(full + st1, ph1);
         PROF_MARK(0);
         // the next step's samples travel while this step waits for its own (sampling only after the
-        // wait costs the lower sweep 40 % on C3 -- measured)
+        // wait costs the lower sweep 40 % on C3 -- measured).  One step of look-ahead: under load a
+        // sample takes ~1600 cycles, about two steps, so every step of every chunk but the lead ones
+        // stalls ~750 cycles on its own (valid) sample -- but sampling two steps ahead finds the
+        // record not written yet and ends in real polls (measured: 15 % slower), and issuing the
+        // step's strong stores behind the next samples instead of in front changes nothing.
         const bool ok2 = (t + 2 < ns) ? mbar_try_wait(full + st2, ph2) : true; // consumed one step from now
         look_ahead(st1, N);
+        PROF_MARK(1);
         if (S.hdr.z & kCwHasExt) { // warp-uniform: the lead chunks of a wavefront never enter
             unsigned pending = 0;
 #pragma unroll
@@ -1657,6 +1668,7 @@ __device__ __forceinline__ void cw_compute(const CwArgs& a, unsigned char* wbase
                 // ago.  At chunk start the producers may be a long way off: poll slowly.
                 int tries = 0;
                 do {
+                    PROF_COUNT(t == 0 ? 11 : 10);
                     if (t == 0)
                         __nanosleep(100);
                     else if (++tries > 4)
@@ -1709,7 +1721,6 @@ __device__ __forceinline__ void cw_compute(const CwArgs& a, unsigned char* wbase
         }
 
         // ---- the step proper: one basic block ---------------------------------------------------
-        PROF_MARK(1);
         const unsigned char* sb = wbase + (size_t)st0 * SM::kStageBytes;
         double rhs[B], yi[B], res[B];
 #pragma unroll

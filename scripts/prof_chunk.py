@@ -14,7 +14,7 @@ s = generators.config(cfg, nx=dims[0], ny=dims[1], nz=dims[2]) if dims else gene
 fs = FlexibleSolver(MatrixAdapter(A), {"preconditioner": {"type": prec}, "b200": {"schedule": "chunks", "prefetch_slices": pf}})
 lib = _lib.lib()
 out = (ctypes.c_ulonglong * 16)()
-names = ["wait full", "look-ahead issue", "ext validate/poll", "compute+stores", "syncwarp+arrive", "loop overhead", "prologue", "wait for chunk start"]
+names = ["late stage wait", "look-ahead issue", "ext validate/poll", "compute+stores", "syncwarp+release", "loop overhead", "prologue", "wait for chunk start"]
 for what, name in ((4, "lower"), (5, "upper")):
     lib.opmb200_prof_read(out, 1)
     ms, nb = fs.time_kernel(what, 0, 10)
@@ -24,4 +24,5 @@ for what, name in ((4, "lower"), (5, "upper")):
     for i in range(8):
         print(f"   {names[i]:20s} {out[i] / max(steps, 1):9.1f}")
     print(f"   {'total':20s} {sum(out[i] for i in range(8)) / max(steps, 1):9.1f}")
+    print(f"   poll-loop iterations per step (t>0): {out[10] / max(steps, 1):.3f}; at chunk start, per chunk: {out[11] / max(warps, 1):.1f}")
 fs.close()
