@@ -19,6 +19,7 @@ iterations/s and time-to-solve are given beside it.
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -232,12 +233,22 @@ def run_b200(args):
         ms, nbytes = fs.time_kernel(what, 3, 20)
         kern[name] = {"ms": round(ms, 4), "algorithmic_MB": round(nbytes / 1e6, 1),
                       "GBps": round(nbytes / ms / 1e6, 1), "frac_of_peak": round(nbytes / ms / 1e6 / peak, 3)}
+    # DRAM traffic per launch of the dominant kernel from the committed ncu --set full capture
+    # (scripts/ncu_traffic.py); null when the capture is of another workload
+    traffic = None
+    caps = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.json")))
+    if caps and args.config == "C3" and args.prec == "dilu" and world == 1:
+        ks = json.load(open(caps[-1]))["kernels"]
+        sw = [v["dram_bytes_per_launch"] for k, v in ks.items() if k.startswith("opmb200::sweep_kernel<3, false") or k.startswith("sweep_kernel<3, 0")]
+        if sw:
+            traffic = round(sum(sw) / len(sw) / 1e6, 1)  # MB per launch, like `achieved`'s numerator
     t_sweep = 0.5 * (kern["sweep_kernel<lower>"]["ms"] + kern["sweep_kernel<upper>"]["ms"])
     b_sweep = 0.5 * (kern["sweep_kernel<lower>"]["algorithmic_MB"] + kern["sweep_kernel<upper>"]["algorithmic_MB"])
     ach = b_sweep / t_sweep  # MB/ms == GB/s
     roofline = {"kernel": "sweep_kernel (DILU lower/upper triangular sweep, 4 launches per iteration)",
                 "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": None, "peak_source": peak_src, "per_kernel": kern}
+                "traffic": traffic, "traffic_unit": "MB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
+                "algorithmic_MB_per_launch": round(b_sweep, 1), "peak_source": peak_src, "per_kernel": kern}
     N, nnzb = info0["n_rows"], info0["nnzb"]
     b_iter = 2 * (nnzb * (8 * b * b + 4) + 4 * (N + 1) + 16 * b * N) \
         + 2 * ((nnzb - N) * (8 * b * b + 4) + 16 * b * b * N + 40 * b * N + 16 * (N + 1) + 8 * N) + 19 * 8 * b * N
