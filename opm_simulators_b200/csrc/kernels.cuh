@@ -1636,8 +1636,12 @@ __device__ __forceinline__ void cw_compute(const CwArgs& a, unsigned char* wbase
         }
     };
 
-    int st0 = 0, st1 = 1 % NS, st2 = 2 % NS; // stages of steps t, t+1, t+2
-    unsigned ph1 = (1 / NS) & 1u, ph2 = (2 / NS) & 1u;
+#ifndef CW_AHEAD
+#define CW_AHEAD 1
+#endif
+    constexpr int A = CW_AHEAD; // steps of look-ahead (dependency samples, own input, column positions)
+    int st0 = 0, st1 = A % NS, st2 = (A + 1) % NS; // stages of steps t, t+A, t+A+1
+    unsigned ph1 = (A / NS) & 1u, ph2 = ((A + 1) / NS) & 1u;
 
     // one step: S is the running step (looked ahead one step ago), N receives the look-ahead of the
     // next one; ok1 tells whether stage st1 (step t+1) had landed when it was tested a step ago.
@@ -1654,7 +1658,7 @@ __device__ __forceinline__ void cw_compute(const CwArgs& a, unsigned char* wbase
         // stalls ~750 cycles on its own (valid) sample -- but sampling two steps ahead finds the
         // record not written yet and ends in real polls (measured: 15 % slower), and issuing the
         // step's strong stores behind the next samples instead of in front changes nothing.
-        const bool ok2 = (t + 2 < ns) ? mbar_try_wait(full + st2, ph2) : true; // consumed one step from now
+        const bool ok2 = (t + A + 1 < ns) ? mbar_try_wait(full + st2, ph2) : true; // consumed one step from now
         look_ahead(st1, N);
         PROF_MARK(1);
         if (S.hdr.z & kCwHasExt) { // warp-uniform: the lead chunks of a wavefront never enter
@@ -1805,7 +1809,8 @@ __device__ __forceinline__ void cw_compute(const CwArgs& a, unsigned char* wbase
         if (lane == 0)
             *progress = t + 1; // releases the stage to the loader
         PROF_MARK(4);
-        st0 = st1;
+        if (++st0 == NS)
+            st0 = 0;
         st1 = st2;
         ph1 = ph2;
         if (++st2 == NS) {
@@ -1819,13 +1824,29 @@ __device__ __forceinline__ void cw_compute(const CwArgs& a, unsigned char* wbase
     PROF_CHUNK(chunk, 0);
     mbar_wait(full + 0, 0u);
     look_ahead(0, SA);
-    bool ok1 = ns > 1 ? mbar_try_wait(full + st1, ph1) : true;
+#if CW_AHEAD == 2
+    CwStep<B> SC;
+    if (ns > 1)
+        mbar_wait(full + 1 % NS, (1 / NS) & 1u);
+    look_ahead(1 % NS, SB);
+#endif
+    bool ok1 = ns > A ? mbar_try_wait(full + st1, ph1) : true;
     PROF_MARK(6);
+#if CW_AHEAD == 2
+    for (int t = 0; t < ns; t += 3) {
+        ok1 = step(t, ok1, SA, SC);
+        if (t + 1 < ns)
+            ok1 = step(t + 1, ok1, SB, SA);
+        if (t + 2 < ns)
+            ok1 = step(t + 2, ok1, SC, SB);
+    }
+#else
     for (int t = 0; t < ns; t += 2) {
         ok1 = step(t, ok1, SA, SB);
         if (t + 1 < ns)
             ok1 = step(t + 1, ok1, SB, SA);
     }
+#endif
     PROF_CHUNK(chunk, 2);
     PROF_FLUSH(ns);
 }

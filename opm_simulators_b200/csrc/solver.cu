@@ -157,12 +157,21 @@ struct opmb200_solver {
     unsigned long long seq = 0;   // reduction sequence number
     int halo_epoch = 0;
 
+    // one BiCGSTAB iteration captured as a CUDA graph (single rank: every kernel argument is fixed
+    // per solver, the scalars live on the device): the launch-bound chain of 9 kernels per iteration
+    // is replayed with one call
+    bool use_graph = true;
+    cudaGraphExec_t iter_graph = nullptr;
+    int64_t iter_graph_launches = 0;
+
     double t_analysis_s = 0, t_update_ms = 0, t_solve_ms = 0;
     int64_t launches = 0;
     std::vector<double> last_hist;
 
     ~opmb200_solver()
     {
+        if (iter_graph)
+            cudaGraphExecDestroy(iter_graph);
         if (h_sc)
             cudaFreeHost(h_sc);
         if (h_small)
@@ -537,6 +546,7 @@ int parse_options(opmb200_solver* s, const char* json)
         s->chunk_rows = prm.get<int>("b200.chunk_rows", 0);
         s->prefetch = std::max(0, std::min(32, prm.get<int>("b200.prefetch_slices", 0)));
         s->debug = prm.get<int>("b200.debug_timing", 0);
+        s->use_graph = prm.get<int>("b200.cuda_graph", 1) != 0;
     } catch (const std::exception& e) {
         return fail(OPMB200_BAD_OPTIONS, e.what());
     }
@@ -629,7 +639,31 @@ int do_solve(opmb200_solver* s, double* x, double* b, double reduction, opmb200_
     while (true) {
         const bool can_enqueue = enq < s->maxiter;
         if (can_enqueue) {
-            TRY(enqueue_iteration(s));
+            if (s->use_graph && s->n_ranks == 1 && s->op_repeats <= 1) {
+                if (!s->iter_graph) {
+                    cudaGraph_t g = nullptr;
+                    const int64_t l0 = s->launches;
+                    CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+                    const int rc = enqueue_iteration(s);
+                    const cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+                    s->iter_graph_launches = s->launches - l0;
+                    s->launches = l0;
+                    if (rc != OPMB200_SUCCESS || ce != cudaSuccess) {
+                        if (g)
+                            cudaGraphDestroy(g);
+                        cudaGetLastError();
+                        return rc != OPMB200_SUCCESS ? rc : fail(OPMB200_CUDA_ERROR, std::string("graph capture: ") + cudaGetErrorString(ce));
+                    }
+                    const cudaError_t ie = cudaGraphInstantiate(&s->iter_graph, g, 0);
+                    cudaGraphDestroy(g);
+                    if (ie != cudaSuccess)
+                        return fail(OPMB200_CUDA_ERROR, std::string("graph instantiate: ") + cudaGetErrorString(ie));
+                }
+                CUDA_TRY(cudaGraphLaunch(s->iter_graph, s->stream));
+                s->launches += s->iter_graph_launches;
+            } else {
+                TRY(enqueue_iteration(s));
+            }
             ++enq;
             const int ns = slot ^ 1;
             CUDA_TRY(cudaMemcpyAsync(&s->h_sc[ns], s->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost, s->stream));
