@@ -242,6 +242,13 @@ def run_b200(args):
         sw = [v["dram_bytes_per_launch"] for k, v in ks.items() if k.startswith("opmb200::sweep_kernel<3, false") or k.startswith("sweep_kernel<3, 0")]
         if sw:
             traffic = round(sum(sw) / len(sw) / 1e6, 1)  # MB per launch, like `achieved`'s numerator
+    per_rank = None
+    if world > 1:  # load balance of the dominant kernel across the ranks
+        mine = {"rank": rank, "levels": info0["n_levels"], "slices": info0["n_slices"], "rows": info0["n_rows"],
+                "lower_ms": kern["sweep_kernel<lower>"]["ms"], "upper_ms": kern["sweep_kernel<upper>"]["ms"],
+                "spmv_ms": kern["spmv_kernel"]["ms"]}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     t_sweep = 0.5 * (kern["sweep_kernel<lower>"]["ms"] + kern["sweep_kernel<upper>"]["ms"])
     b_sweep = 0.5 * (kern["sweep_kernel<lower>"]["algorithmic_MB"] + kern["sweep_kernel<upper>"]["algorithmic_MB"])
     ach = b_sweep / t_sweep  # MB/ms == GB/s
@@ -276,6 +283,8 @@ def run_b200(args):
                     "device_ms_per_step": round(ms_e2e / args.steps, 4)},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
         }
+        if per_rank:
+            out["per_rank"] = per_rank
     # ---- CPU baseline (rank 0, single-GPU run only) -------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_port_baseline(w, args)

@@ -1134,6 +1134,23 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                 for (int e = 0; e < BB; ++e)
                     blk[s][e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
             }
+        // first slot beyond the register window (e.g. the ghost plane below a rank's slab, which the
+        // ghost-last numbering turns into a 4th upper entry of 13 200 rows): its dependency is sampled
+        // with the others and its block copied into shared memory now (cp.async, no registers held)
+        // -- handled one after the other behind the wait it cost the upper sweep of such a rank +45 %
+        __shared__ double xblk[kWarpsPerCta][BB * 32];
+        int cjx = -1;
+        if (active && w > kPrefetch) {
+            cjx = __ldg(a.slot_col + (size_t)(sr0 + kPrefetch) * 32 + lane);
+            if (cjx >= 0) {
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(
+                                     &xblk[threadIdx.x >> 5][e * 32 + lane])),
+                                 "l"(a.M + elem_index<BB>(sr0 + kPrefetch, lane, e))
+                                 : "memory");
+            }
+        }
         double di[BB], rhs[B], yi[B];
         bool ghost = false;
         if (active) {
@@ -1173,12 +1190,14 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
 
         // ---- 3. wait for the rows this row depends on, then accumulate in slot order ------------
         if (active) {
-            double xv[kPrefetch][B];
+            double xv[kPrefetch][B], xvx[B];
             unsigned pending = 0;
 #pragma unroll
             for (int s = 0; s < kPrefetch; ++s)
                 if (cj[s] >= 0)
                     pending |= 1u << s;
+            if (cjx >= 0)
+                pending |= 1u << kPrefetch;
             while (pending) {
                 // all outstanding dependencies are sampled together, one strong vector load each;
                 // every word validates itself against the sentinel
@@ -1186,10 +1205,14 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                 for (int s = 0; s < kPrefetch; ++s)
                     if (pending & (1u << s))
                         rec_load_strong<B>(out, (size_t)cj[s], xv[s]);
+                if (pending & (1u << kPrefetch))
+                    rec_load_strong<B>(out, (size_t)cjx, xvx);
 #pragma unroll
                 for (int s = 0; s < kPrefetch; ++s)
                     if ((pending & (1u << s)) && rec_valid<B>(xv[s]))
                         pending &= ~(1u << s);
+                if ((pending & (1u << kPrefetch)) && rec_valid<B>(xvx))
+                    pending &= ~(1u << kPrefetch);
             }
 #pragma unroll
             for (int s = 0; s < kPrefetch; ++s)
@@ -1201,16 +1224,26 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                 }
             // rows wider than the register window (NNC / well rows): stream the rest
             for (int s = kPrefetch; s < w; ++s) {
-                const int c = __ldg(a.slot_col + (size_t)(sr0 + s) * 32 + lane);
+                const int c = s == kPrefetch ? cjx : __ldg(a.slot_col + (size_t)(sr0 + s) * 32 + lane);
                 if (c < 0)
                     continue;
                 double bl[BB], xs[B];
+                if (s == kPrefetch) {
+                    asm volatile("cp.async.wait_all;" ::: "memory");
 #pragma unroll
-                for (int e = 0; e < BB; ++e)
-                    bl[e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
-                do {
-                    rec_load_strong<B>(out, (size_t)c, xs);
-                } while (!rec_valid<B>(xs));
+                    for (int e = 0; e < BB; ++e)
+                        bl[e] = xblk[threadIdx.x >> 5][e * 32 + lane]; // this lane's own copies
+#pragma unroll
+                    for (int r = 0; r < B; ++r)
+                        xs[r] = xvx[r]; // sampled with the first kPrefetch dependencies
+                } else {
+#pragma unroll
+                    for (int e = 0; e < BB; ++e)
+                        bl[e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
+                    do {
+                        rec_load_strong<B>(out, (size_t)c, xs);
+                    } while (!rec_valid<B>(xs));
+                }
                 if (UPPER && !ILU0)
                     blk_umv<B>(bl, xs, rhs);
                 else

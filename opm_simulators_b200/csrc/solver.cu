@@ -164,6 +164,12 @@ struct opmb200_solver {
     cudaGraphExec_t iter_graph = nullptr;
     int64_t iter_graph_launches = 0;
 
+    // OPMB200_TRACE=1: CUDA events between the stages of every iteration, summed per stage and
+    // printed at the end of each solve (where does a multi-rank iteration spend its time?)
+    bool trace = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
+    size_t trace_used = 0;
+
     double t_analysis_s = 0, t_update_ms = 0, t_solve_ms = 0;
     int64_t launches = 0;
     std::vector<double> last_hist;
@@ -407,6 +413,8 @@ int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
     return check_launch(s, upper ? "upper sweep" : "lower sweep");
 }
 
+void trace_mark(opmb200_solver* s, const char* name);
+
 // Preconditioner::apply(v, d) on level-ordered device vectors, incl. BlockPreconditioner's halo copy
 int prec_apply(opmb200_solver* s, const double* d, double* v, int ghost_zero, int check_done)
 {
@@ -417,6 +425,7 @@ int prec_apply(opmb200_solver* s, const double* d, double* v, int ghost_zero, in
     const SweepArgs a = sweep_args(s, d, v, ghost_zero, check_done);
     TRY(launch_sweep(s, a, false));
     TRY(launch_sweep(s, a, true));
+    trace_mark(s, "sweeps");
     TRY(copy_owner_to_all(s, v));
     if (s->prec == PREC_ILU0 && std::abs(s->relaxation - 1.0) > 1e-15) {
         scale_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->len(), s->relaxation, v, s->sc.p, check_done);
@@ -547,6 +556,7 @@ int parse_options(opmb200_solver* s, const char* json)
         s->prefetch = std::max(0, std::min(32, prm.get<int>("b200.prefetch_slices", 0)));
         s->debug = prm.get<int>("b200.debug_timing", 0);
         s->use_graph = prm.get<int>("b200.cuda_graph", 1) != 0;
+        s->trace = std::getenv("OPMB200_TRACE") != nullptr;
     } catch (const std::exception& e) {
         return fail(OPMB200_BAD_OPTIONS, e.what());
     }
@@ -582,22 +592,65 @@ VecArgs vec_args(opmb200_solver* s, bool reduces)
     return a;
 }
 
+void trace_mark(opmb200_solver* s, const char* name)
+{
+    if (!s->trace)
+        return;
+    if (s->trace_used == s->trace_ev.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        s->trace_ev.emplace_back(name, e);
+    }
+    s->trace_ev[s->trace_used].first = name;
+    cudaEventRecord(s->trace_ev[s->trace_used++].second, s->stream);
+}
+
+void trace_report(opmb200_solver* s)
+{
+    if (!s->trace || s->trace_used < 2)
+        return;
+    std::vector<std::pair<std::string, double>> sum;
+    for (size_t i = 1; i < s->trace_used; ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, s->trace_ev[i - 1].second, s->trace_ev[i].second);
+        const std::string name = s->trace_ev[i].first;
+        auto it = std::find_if(sum.begin(), sum.end(), [&](auto& p) { return p.first == name; });
+        if (it == sum.end())
+            sum.emplace_back(name, ms);
+        else
+            it->second += ms;
+    }
+    std::string line = "[opmb200 trace rank " + std::to_string(s->comm ? s->comm->rank : 0) + "] ms per solve:";
+    for (auto& p : sum)
+        line += " " + p.first + "=" + std::to_string(p.second);
+    std::fprintf(stderr, "%s\n", line.c_str());
+    s->trace_used = 0;
+}
+
 // one BiCGSTAB iteration (two half steps) enqueued on the stream
 int enqueue_iteration(opmb200_solver* s)
 {
     const int gz = 1; // Dune: y = 0 before every preconditioner application
+    trace_mark(s, "iteration_begin");
     vec_p_update_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, false));
     TRY(check_launch(s, "vec_p_update"));
+    trace_mark(s, "vec_p_update");
     TRY(prec_apply(s, s->vp.p, s->vy.p, gz, 1));                       // y = W^-1 p
+    trace_mark(s, "prec_apply+halo");
     TRY(op_apply(s, s->vy.p, s->vv.p, 1, s->vrt.p, EPI_H, 1));          // v = A y ; h = (rt, v)
+    trace_mark(s, "spmv+allreduce");
     vec_half1_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, true)); // x += alpha y ; r -= alpha v ; |r|
     TRY(check_launch(s, "vec_half1"));
     TRY(finish_reduction(s, 1, EPI_NORM1, 1));
+    trace_mark(s, "vec_half+allreduce");
     TRY(prec_apply(s, s->vr.p, s->vy.p, gz, 1));                       // y = W^-1 r
+    trace_mark(s, "prec_apply+halo");
     TRY(op_apply(s, s->vy.p, s->vt.p, 2, s->vr.p, EPI_OMEGA, 1));       // t = A y ; (t,r), (t,t)
+    trace_mark(s, "spmv+allreduce");
     vec_half2_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, true)); // x += omega y ; r -= omega t ; |r| ; (rt,r)
     TRY(check_launch(s, "vec_half2"));
     TRY(finish_reduction(s, 2, EPI_NORM2, 1));
+    trace_mark(s, "vec_half+allreduce");
     return OPMB200_SUCCESS;
 }
 
@@ -639,7 +692,7 @@ int do_solve(opmb200_solver* s, double* x, double* b, double reduction, opmb200_
     while (true) {
         const bool can_enqueue = enq < s->maxiter;
         if (can_enqueue) {
-            if (s->use_graph && s->n_ranks == 1 && s->op_repeats <= 1) {
+            if (s->use_graph && s->n_ranks == 1 && s->op_repeats <= 1 && !s->trace) {
                 if (!s->iter_graph) {
                     cudaGraph_t g = nullptr;
                     const int64_t l0 = s->launches;
@@ -687,6 +740,7 @@ int do_solve(opmb200_solver* s, double* x, double* b, double reduction, opmb200_
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
     s->t_solve_ms = ms;
+    trace_report(s);
     // final state (the early-exit kernels leave it untouched once done is set)
     CUDA_TRY(cudaMemcpy(&fin, s->sc.p, sizeof(Scalars), cudaMemcpyDeviceToHost));
     s->last_hist.assign(std::max(fin.hist_count, 0), 0.0);
