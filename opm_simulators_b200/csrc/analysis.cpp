@@ -586,6 +586,24 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
             L.trip_dst.assign(tot, -1);
         }
     }
+    if (want_ilu0) {
+        L.row_static.assign(n, 1);
+        for (int s = 0; s < L.n_slices; ++s) {
+            const int64_t gd0 = ((int64_t)L.slice_base[s] + L.slice_wl[s]) * kSlice;
+            for (int32_t q = L.slice_q0[s]; q < L.slice_q0[s + 1]; ++q) {
+                const int lane = q - L.slice_q0[s];
+                const int64_t i = L.r2n[q];
+                if (i >= n_interior)
+                    continue;
+                for (int sl = 0; sl < diag[i] - rowptr[i]; ++sl) {
+                    const int64_t cl = ((int64_t)L.slice_lrank[s] + sl) * kSlice + lane;
+                    for (int32_t t = L.trip_ptr[cl]; t < L.trip_ptr[cl + 1]; ++t)
+                        if (L.trip_dst[t] != gd0 + lane)
+                            L.row_static[q] = 0;
+                }
+            }
+        }
+    }
     return OPMB200_SUCCESS;
 }
 

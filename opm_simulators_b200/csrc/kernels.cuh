@@ -799,9 +799,10 @@ struct FactorArgs {
     const int* trip_ptr;    // ILU0
     const int* trip_src;
     const int* trip_dst;
+    const int* row_static;  // ILU0: the row's U blocks are never modified (by position)
     double* dinv;           // [n][b*b] by position
     double* dinv_s;         // the same in slice layout [slice][b*b][32] (what the chunk sweeps stage)
-    double* dinv_rec;       // DILU factorisation: Dinv as dependency records [n][b][Rec<b>::W]
+    double* dinv_rec;       // Dinv as dependency records [n][b][Rec<b>::W] (sentinel-armed before the launch)
     int* row_flag;          // [n]
     int epoch;
     Ticket ticket;
@@ -941,8 +942,11 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
         if (lane < m.count) {
             const int q = m.q0 + lane;
             // Fast path (7-point-like rows): at most kPrefetch lower blocks, each of which updates only
-            // the diagonal.  Everything is gathered with a few batched loads: own blocks before the
-            // wait, the neighbours' Dinv_j and U_ji after it.
+            // the diagonal, with rows whose own elimination only ever touched THEIR diagonal.  Then
+            // U_ji still holds the caller's value and is read -- like the row's own blocks -- before
+            // the wait; the only thing that travels from row to row is Dinv_j, as sentinel-armed
+            // dependency records sampled with B strong vector loads (the DILU factorisation's scheme:
+            // 27 + 27 separate strong 8-byte loads behind a flag made this kernel 3.8 ms on C3).
             bool fast = m.wl <= kPrefetch;
             int cj[kPrefetch], tsrc[kPrefetch];
             const int gdiag = (m.base + m.wl) * 32 + lane;
@@ -957,38 +961,58 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
                         const int t0 = a.trip_ptr[cl], t1 = a.trip_ptr[cl + 1];
                         if (t1 - t0 > 1 || (t1 - t0 == 1 && a.trip_dst[t0] != gdiag))
                             fast = false;
-                        else if (t1 - t0 == 1)
+                        else if (t1 - t0 == 1) {
                             tsrc[k] = a.trip_src[t0];
+                            if (!a.row_static[cj[k]])
+                                fast = false;
+                        }
                     }
                 }
             }
             if (fast) {
-                double Aij[kPrefetch][BB], D[BB];
-#pragma unroll
-                for (int k = 0; k < kPrefetch; ++k)
-                    if (cj[k] >= 0) {
-#pragma unroll
-                        for (int e = 0; e < BB; ++e)
-                            Aij[k][e] = a.F[elem_index<BB>(m.base + k, lane, e)];
-                    }
-#pragma unroll
-                for (int e = 0; e < BB; ++e)
-                    D[e] = a.F[elem_index<BB>(m.base + m.wl, lane, e)];
-#pragma unroll
-                for (int k = 0; k < kPrefetch; ++k)
-                    if (cj[k] >= 0)
-                        while (ld_relaxed(a.row_flag + cj[k]) != a.epoch) {}
-                __threadfence();
-                double Dj[kPrefetch][BB], Uji[kPrefetch][BB];
+                double Aij[kPrefetch][BB], Uji[kPrefetch][BB], D[BB];
 #pragma unroll
                 for (int k = 0; k < kPrefetch; ++k)
                     if (cj[k] >= 0) {
 #pragma unroll
                         for (int e = 0; e < BB; ++e) {
-                            Dj[k][e] = __ldcg(a.dinv + (size_t)cj[k] * BB + e);
-                            Uji[k][e] = tsrc[k] >= 0 ? __ldcg(a.F + elem_index_slot<BB>(tsrc[k], e)) : 0.0;
+                            Aij[k][e] = a.F[elem_index<BB>(m.base + k, lane, e)];
+                            Uji[k][e] = tsrc[k] >= 0 ? a.F[elem_index_slot<BB>(tsrc[k], e)] : 0.0;
                         }
                     }
+#pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    D[e] = a.F[elem_index<BB>(m.base + m.wl, lane, e)];
+                double Dj[kPrefetch][BB];
+                unsigned pending = 0;
+#pragma unroll
+                for (int k = 0; k < kPrefetch; ++k)
+                    if (cj[k] >= 0)
+                        pending |= 1u << k;
+                while (pending) {
+#pragma unroll
+                    for (int k = 0; k < kPrefetch; ++k)
+                        if (pending & (1u << k)) {
+#pragma unroll
+                            for (int r = 0; r < B; ++r) {
+                                double row[B];
+                                rec_load_strong<B>(a.dinv_rec, (size_t)cj[k] * B + r, row);
+#pragma unroll
+                                for (int c2 = 0; c2 < B; ++c2)
+                                    Dj[k][r * B + c2] = row[c2];
+                            }
+                        }
+#pragma unroll
+                    for (int k = 0; k < kPrefetch; ++k)
+                        if (pending & (1u << k)) {
+                            bool ok = true;
+#pragma unroll
+                            for (int e = 0; e < BB; ++e)
+                                ok = ok && !is_sentinel(Dj[k][e]);
+                            if (ok)
+                                pending &= ~(1u << k);
+                        }
+                }
 #pragma unroll
                 for (int k = 0; k < kPrefetch; ++k)
                     if (cj[k] >= 0) {
@@ -1007,12 +1031,23 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
                 if (!blk_invert<B>(D))
                     a.sc->factor_error = 1;
 #pragma unroll
+                for (int e = 0; e < BB; ++e)
+                    D[e] = guard(D[e]);
+#pragma unroll
+                for (int r = 0; r < B; ++r) { // publish Dinv first: that is what the next rows wait for
+                    double row[B];
+#pragma unroll
+                    for (int c2 = 0; c2 < B; ++c2)
+                        row[c2] = D[r * B + c2];
+                    rec_store_strong<B>(a.dinv_rec, (size_t)q * B + r, row);
+                }
+#pragma unroll
                 for (int e = 0; e < BB; ++e) {
                     a.F[elem_index<BB>(m.base + m.wl, lane, e)] = D[e];
                     a.dinv[(size_t)q * BB + e] = D[e];
                     a.dinv_s[((size_t)S * BB + e) * 32 + lane] = D[e];
                 }
-                __threadfence();
+                __threadfence(); // rows on the general path wait for the flag and read F and dinv
                 st_relaxed(a.row_flag + q, a.epoch);
                 goto row_done;
             }
@@ -1060,13 +1095,22 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
                 a.sc->factor_error = 1;
 #pragma unroll
             for (int e = 0; e < BB; ++e) {
+                D[e] = guard(D[e]);
                 a.F[elem_index<BB>(m.base + m.wl, lane, e)] = D[e];
                 a.dinv[(size_t)q * BB + e] = D[e];
                 a.dinv_s[((size_t)S * BB + e) * 32 + lane] = D[e];
             }
-            // 3. publish: release fence, then the flag
+            // 3. publish: release fence, then the flag and the Dinv records the fast rows wait for
             __threadfence();
             st_relaxed(a.row_flag + q, a.epoch);
+#pragma unroll
+            for (int r = 0; r < B; ++r) {
+                double row[B];
+#pragma unroll
+                for (int c2 = 0; c2 < B; ++c2)
+                    row[c2] = D[r * B + c2];
+                rec_store_strong<B>(a.dinv_rec, (size_t)q * B + r, row);
+            }
         row_done:;
         }
     }

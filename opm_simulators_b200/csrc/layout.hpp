@@ -70,6 +70,9 @@ struct Layout {
     // ILU0: per compact L slot, the (source slot in row j, destination slot in row i) update pairs
     std::vector<int32_t> trip_ptr; // [n_l_slot_rows*32 + 1]
     std::vector<int32_t> trip_src, trip_dst;
+    // ILU0: 1 where the elimination of a row (by position) only ever updates its own diagonal block,
+    // i.e. its U blocks stay the caller's values and may be read before the row is finished
+    std::vector<int32_t> row_static; // [n]
 
     int64_t n_l_slot_rows() const { return slice_lrank.empty() ? 0 : slice_lrank.back(); }
 };

@@ -130,7 +130,7 @@ struct opmb200_solver {
     int epoch = 0;
 
     DevBuf<SliceMeta> slices;
-    DevBuf<int> slot_col, slot_src, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag, chunk_slice0;
+    DevBuf<int> slot_col, slot_src, row_static, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag, chunk_slice0;
     DevBuf<double> A, F, dinv, dinv_s, dinv_rec, vals_native;
     DevBuf<unsigned char> stream_lo, stream_up; // chunk schedule: step records of the lower / upper sweep
     DevBuf<double> vx, vr, vp, vv, vt, vy, vrt, vw, nat0, nat1;
@@ -449,6 +449,7 @@ int prec_update(opmb200_solver* s)
     a.trip_ptr = s->trip_ptr.p;
     a.trip_src = s->trip_src.p;
     a.trip_dst = s->trip_dst.p;
+    a.row_static = s->row_static.p;
     a.dinv = s->dinv.p;
     a.dinv_s = s->dinv_s.p;
     a.dinv_rec = s->dinv_rec.p;
@@ -457,7 +458,7 @@ int prec_update(opmb200_solver* s)
     a.ticket = s->ticket();
     a.sc = s->sc.p;
     const int grid = s->slice_grid();
-    if (s->prec == PREC_DILU) { // arm the Dinv dependency records
+    { // arm the Dinv dependency records
         fill_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->dinv_rec.p, (int64_t)s->dinv_rec.n, sentinel_host());
         TRY(check_launch(s, "fill"));
     }
@@ -994,12 +995,12 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
         CUDA_TRY(s->trip_ptr.upload(L.trip_ptr, st));
         CUDA_TRY(s->trip_src.upload(L.trip_src, st));
         CUDA_TRY(s->trip_dst.upload(L.trip_dst, st));
+        CUDA_TRY(s->row_static.upload(L.row_static, st));
         CUDA_TRY(s->F.alloc((size_t)L.n_slot_rows * kSlice * BB));
     }
     CUDA_TRY(s->A.alloc((size_t)L.n_slot_rows * kSlice * BB));
     CUDA_TRY(s->dinv.alloc((size_t)L.n * BB));
-    if (s->prec == PREC_DILU)
-        CUDA_TRY(s->dinv_rec.alloc((size_t)L.n * block_size * (block_size <= 2 ? 2 : 4)));
+    CUDA_TRY(s->dinv_rec.alloc((size_t)L.n * block_size * (block_size <= 2 ? 2 : 4)));
     CUDA_TRY(s->dinv_s.alloc((size_t)std::max(L.n_slices, 1) * kSlice * BB));
     CUDA_TRY(cudaMemsetAsync(s->dinv_s.p, 0, s->dinv_s.n * sizeof(double), st));
     CUDA_TRY(s->row_flag.alloc((size_t)L.n));
