@@ -581,12 +581,24 @@ __device__ __forceinline__ void grid_reduce(double (&v)[ND], const ReduceCtx& rc
     if (!is_last)
         return;
     __threadfence();
+    // the other CTAs' partials must come from the L2 (this SM's L1 may hold the previous reduction's);
+    // L1-bypassing loads are slow one by one (~300 cycles each beyond a few in flight), so four
+    // partials per strong vector load (rc.stride is a multiple of 4), in a fixed order
     double acc[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) {
         acc[d] = 0.0;
-        for (unsigned int i = threadIdx.x; i < gridDim.x; i += blockDim.x)
-            acc[d] += __ldcg(&rc.partials[d * rc.stride + i]);
+        const double* p = rc.partials + (size_t)d * rc.stride;
+        const unsigned int n4 = gridDim.x >> 2;
+        for (unsigned int g = threadIdx.x; g < n4; g += blockDim.x) {
+            double w0, w1, w2, w3;
+            asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                         : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3)
+                         : "l"(p + 4 * (size_t)g));
+            acc[d] += (w0 + w1) + (w2 + w3);
+        }
+        for (unsigned int i = (n4 << 2) + threadIdx.x; i < gridDim.x; i += blockDim.x)
+            acc[d] += __ldcg(p + i);
     }
     __syncthreads();
     cta_sum<ND>(acc, red_smem);

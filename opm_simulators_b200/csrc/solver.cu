@@ -1012,7 +1012,7 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
         CUDA_TRY(cudaMemsetAsync(v->p, 0, std::max<size_t>(len, 1) * sizeof(double), st));
     }
     s->vec_grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)s->num_sms * 8, ((int64_t)len + 255) / 256));
-    s->max_grid = std::max(s->vec_grid, s->slice_grid());
+    s->max_grid = (std::max(s->vec_grid, s->slice_grid()) + 3) & ~3; // multiple of 4: grid_reduce reads 4 partials per load
     CUDA_TRY(s->partials.alloc((size_t)2 * s->max_grid));
     CUDA_TRY(s->hist.alloc((size_t)2 * s->maxiter + 4));
     CUDA_TRY(s->sums.alloc(4));
