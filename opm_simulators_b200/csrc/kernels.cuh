@@ -126,6 +126,25 @@ __device__ __forceinline__ void rec_load_strong(const double* base, size_t q, do
             x[3] = w3;
     }
 }
+// weak load of a record written by an EARLIER kernel (the lower sweep's y read by the upper sweep).
+// NOT __ldcg: ld.global.cg compiles to LDG.STRONG.GPU, and the hardware serialises strong loads
+// (~330 cycles each beyond the first few in flight, scripts/microbench_hop.cu)
+template <int B>
+__device__ __forceinline__ void rec_load_weak(const double* base, size_t q, double (&x)[B])
+{
+    const double2* p = reinterpret_cast<const double2*>(base + q * Rec<B>::W);
+    const double2 a = __ldcs(p);
+    x[0] = a.x;
+    if constexpr (B >= 2)
+        x[1] = a.y;
+    if constexpr (B >= 3) {
+        const double2 b = __ldcs(p + 1);
+        x[2] = b.x;
+        if constexpr (B == 4)
+            x[3] = b.y;
+    }
+}
+
 template <int B>
 __device__ __forceinline__ void rec_store_strong(double* base, size_t q, const double (&x)[B])
 {
@@ -888,6 +907,7 @@ __global__ void __launch_bounds__(kCtaThreads) dilu_factor_kernel(FactorArgs a)
                                     Dj[k][r * B + c2] = row[c2];
                             }
                         }
+                    unsigned got = 0;
 #pragma unroll
                     for (int k = 0; k < kPrefetch; ++k)
                         if (pending & (1u << k)) {
@@ -896,8 +916,9 @@ __global__ void __launch_bounds__(kCtaThreads) dilu_factor_kernel(FactorArgs a)
                             for (int e = 0; e < BB; ++e)
                                 ok = ok && !is_sentinel(Dj[k][e]);
                             if (ok)
-                                pending &= ~(1u << k);
+                                got |= 1u << k;
                         }
+                    pending &= ~got;
                 }
 #pragma unroll
                 for (int k = 0; k < kPrefetch; ++k)
@@ -1014,6 +1035,7 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
                                     Dj[k][r * B + c2] = row[c2];
                             }
                         }
+                    unsigned got = 0;
 #pragma unroll
                     for (int k = 0; k < kPrefetch; ++k)
                         if (pending & (1u << k)) {
@@ -1022,8 +1044,9 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
                             for (int e = 0; e < BB; ++e)
                                 ok = ok && !is_sentinel(Dj[k][e]);
                             if (ok)
-                                pending &= ~(1u << k);
+                                got |= 1u << k;
                         }
+                    pending &= ~got;
                 }
 #pragma unroll
                 for (int k = 0; k < kPrefetch; ++k)
@@ -1224,7 +1247,7 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
                     rhs[r] = ghost ? (a.ghost_zero ? 0.0 : a.v[VIDX(a.n, q, r)]) : a.d[VIDX(a.n, q, r)];
                 rec_store_sentinel<B>(a.vpoll, (size_t)q); // arm the upper sweep's records
             } else {
-                rec_load_strong<B>(a.tmp, (size_t)q, yi); // y_i of the lower sweep (complete: previous kernel)
+                rec_load_weak<B>(a.tmp, (size_t)q, yi); // y_i of the lower sweep (complete: previous kernel)
 #pragma unroll
                 for (int r = 0; r < B; ++r)
                     rhs[r] = (ILU0) ? yi[r] : 0.0;
@@ -1500,25 +1523,6 @@ __device__ __forceinline__ void rec_load_ahead(const double* base, size_t q, dou
             x[3] = w3;
     }
 }
-// weak load of a record written by an EARLIER kernel (the lower sweep's y read by the upper sweep).
-// NOT __ldcg: ld.global.cg compiles to LDG.STRONG.GPU, and the hardware serialises strong loads
-// (~330 cycles each beyond the first few in flight, scripts/microbench_hop.cu)
-template <int B>
-__device__ __forceinline__ void rec_load_weak(const double* base, size_t q, double (&x)[B])
-{
-    const double2* p = reinterpret_cast<const double2*>(base + q * Rec<B>::W);
-    const double2 a = __ldcs(p);
-    x[0] = a.x;
-    if constexpr (B >= 2)
-        x[1] = a.y;
-    if constexpr (B >= 3) {
-        const double2 b = __ldcs(p + 1);
-        x[2] = b.x;
-        if constexpr (B == 4)
-            x[3] = b.y;
-    }
-}
-
 // the BB values of lane `lane` in a block slot of a stage (shared memory)
 template <int BB>
 __device__ __forceinline__ void cw_load_slot(const unsigned char* slot, int lane, double (&v)[BB])

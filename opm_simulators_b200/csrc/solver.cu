@@ -117,7 +117,7 @@ struct opmb200_solver {
     int maxiter = 200;
     int verbosity = 0;
     int op_repeats = 1;
-    int throttle = 3;
+    int throttle = 6;
     int schedule = 0;   // 0 levels, 1 chunks
     int chunk_rows = 0; // <= 0: automatic
     int prefetch = 0;   // L2 look-ahead of the chunk sweeps' loader warps, in steps
@@ -548,7 +548,7 @@ int parse_options(opmb200_solver* s, const char* json)
             return fail(OPMB200_BAD_OPTIONS, "preconditioner.mixed_precision_scheme != 0 is outside this path");
         s->relaxation = prm.get<double>("preconditioner.relaxation", 1.0);
         s->op_repeats = prm.get<int>("b200.operator_repeats", 1);
-        s->throttle = prm.get<int>("b200.throttle_levels", 3);
+        s->throttle = prm.get<int>("b200.throttle_levels", 6);
         const std::string sched = prm.get<std::string>("b200.schedule", "levels");
         if (sched != "levels" && sched != "chunks")
             return fail(OPMB200_BAD_OPTIONS, "b200.schedule must be \"levels\" or \"chunks\"");
