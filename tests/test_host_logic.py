@@ -288,3 +288,31 @@ def test_chunk_schedule_falls_back_when_tiles_would_deadlock():
     A = s["A"]
     P = _plan(A, 1, 0)
     _check_schedule(A, P, True)
+
+
+def test_schedules_with_ghost_rows_and_degenerate_patterns():
+    """ghost-last local systems (identity ghost rows behind the owners) and tiny patterns through every schedule"""
+    rng = np.random.default_rng(9)
+    full = generators.blackoil_system(10, 12, 8, b=2, seed=8, with_rhs=False)["A"]
+    part = partition.partition_simple(full.n, 2)
+    for rank in (0, 1):
+        ls = partition.localize(full, part, rank)
+        for sched, cr in ((0, 0), (1, 0), (1, 128), (1, -804)):
+            P = _plan(ls.A, sched, cr, n_interior=ls.n_interior)
+            assert sorted(P["r2n"].tolist()) == list(range(ls.A.n))
+            # owner rows: every lower neighbour sits in an earlier slice; ghost rows depend on nothing
+            pos = np.empty(ls.A.n, np.int64)
+            pos[P["r2n"]] = np.arange(ls.A.n)
+            sl = np.searchsorted(P["slice_first"], pos, side="right") - 1
+            rows = np.repeat(np.arange(ls.A.n), np.diff(ls.A.rowptr))
+            own_lo = (ls.A.col < rows) & (rows < ls.n_interior)
+            assert (sl[ls.A.col[own_lo]] < sl[rows[own_lo]]).all()
+            if sched == 1:
+                ch = np.searchsorted(P["chunk_first"], sl, side="right") - 1
+                own = rows < ls.n_interior
+                lo, hi = own & (ls.A.col < rows), own & (ls.A.col > rows)
+                assert (ch[ls.A.col[lo]] <= ch[rows[lo]]).all() and (ch[ls.A.col[hi]] >= ch[rows[hi]]).all()
+    one = pattern_to_bcsr([[0]], 3, rng)
+    for sched in (0, 1):
+        P = _plan(one, sched)
+        assert P["n_slices"] == 1 and P["r2n"].tolist() == [0]
