@@ -93,7 +93,7 @@ typedef struct opmb200_info {
     double t_update_ms;    /* device time of the last update_values (H2D + relayout + factorise)   */
     double t_solve_ms;     /* device time of the last solve                                        */
     int64_t kernel_launches; /* kernels launched by this handle so far                             */
-    int schedule;          /* 0 level-scheduled sweeps, 1 chunked wavefronts                       */
+    int schedule;          /* what was built: 0 level-scheduled sweeps, 1 tile walkers              */
     int n_chunks;          /* chunks of the chunked schedule                                       */
     int chunk_rows;        /* rows per chunk (chosen by the analysis when not given)               */
     double est_steps;      /* analysis estimate of the sweep length in local steps                 */
@@ -112,17 +112,28 @@ int opmb200_set_device(int device);
 int opmb200_row_coloring(int64_t n, const int32_t* rowptr, const int32_t* colidx, int type,
                          int32_t* color, int32_t* level_rows, int32_t* level_ptr, int32_t* n_levels);
 /* The sweep schedule of a sparsity pattern, host only (what opmb200_create builds; the threaded
- * reference orders rows by level set, DILU.hpp:82-91, 306-363).  schedule 0 = level sets, 1 = chunked
- * wavefronts (chunk_rows > 0 forces contiguous chunks of that many rows, <= 0 chooses; box grids get
- * tiles of 32 grid lines, reported as chunk_rows = -(TJ*100+TK)).  position_to_row[n]: rows in
- * schedule order; slice_first[n+1] (first *n_slices+1 valid): first position of every 32-row slice
- * (= one step of one warp); chunk_first_slice[n+2] (first *n_chunks+1 valid; schedule 1 only).
+ * reference orders rows by level set, DILU.hpp:82-91, 306-363).  schedule 0 = level sets, 1 = tiles
+ * (chunk_rows > 0 forces contiguous chunks of that many rows, 0 chooses, -(TJ*100+TK) forces that tile
+ * shape; box grids get tiles of TJ x TK grid lines, reported as chunk_rows = -(TJ*100+TK)), 2 = auto
+ * (tiles on box grids whose rows have at most 4 lower / upper blocks, else level sets; *schedule_out
+ * tells).  position_to_row[n]: rows in schedule order; slice_first[n+1] (first *n_slices+1 valid):
+ * first position of every <= 32-row slice; chunk_first_slice[n+2] (first *n_chunks+1 valid; tiles only).
  * Invariant the sweeps rely on: a row depends only on rows of earlier slices, and only on rows of
  * the same or an earlier chunk.  Output pointers may be NULL. */
 int opmb200_plan_schedule(int block_size, int64_t n_rows, int64_t nnzb, const int32_t* rowptr, const int32_t* colidx,
                           int64_t n_interior, int schedule, int chunk_rows, int32_t* n_slices, int32_t* n_chunks,
                           int32_t* chunk_rows_out, double* est_steps, int32_t* position_to_row, int32_t* slice_first,
                           int32_t* chunk_first_slice);
+/* The step tables of the tile walkers for the same arguments, host only (tests replay them on the CPU).
+ * info[8] = {schedule built, rows per step R, ring positions, dependency slots lower, upper, n_steps,
+ * n_chunks, chunk_rows}.  With info[0] == 1 and non-NULL pointers: step_first[n_steps+1] positions,
+ * chunk_first_step[n_chunks+1], step_flags[n_steps] (bit 0: ghost rows) and, for `direction` (0 lower,
+ * 1 upper) with S slots and RP = (R+3)&~3: codes[n_steps*S*RP] (-1 none | 1<<30 + ring index | 1<<29 +
+ * external slot), ext[n_steps*32] positions, n_ext[n_steps].  Call once with NULL arrays to size. */
+int opmb200_plan_tiles(int block_size, int64_t n_rows, int64_t nnzb, const int32_t* rowptr, const int32_t* colidx,
+                       int64_t n_interior, int schedule, int chunk_rows, int32_t* info, int32_t* position_to_row,
+                       int32_t* step_first, int32_t* chunk_first_step, int32_t* step_flags, int direction,
+                       int32_t* codes, int32_t* ext, int32_t* n_ext);
 /* Opm::partitionCellsSimple (opm/simulators/flow/partitionCells.cpp:734-751) */
 int opmb200_partition_simple(int32_t num_cells, int32_t num_domains, int32_t* part);
 /* Ghost-last local system of one rank with one overlap layer (FlowGenericVanguard.hpp:79,

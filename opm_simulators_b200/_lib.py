@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libopmb200.so")
+# OPMB200_LIB: a differently built copy of the SAME library (design experiments, e.g. -fmad=false)
+LIB_PATH = os.environ.get("OPMB200_LIB") or os.path.join(HERE, "libopmb200.so")
 
 SUCCESS, INVALID_ARGUMENT, BAD_OPTIONS, MATRIX_BLOCK_ERROR, SOLVER_ABORT, CUDA_ERROR, NCCL_ERROR, \
     DIAGONAL_MISSING, NOT_PREPARED = range(9)
@@ -58,6 +59,8 @@ PROTOTYPES = {
     "opmb200_plan_schedule": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _i32p, _i32p, C.c_int64, C.c_int, C.c_int,
                                          C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                          C.POINTER(C.c_double), _vp, _vp, _vp]),
+    "opmb200_plan_tiles": (C.c_int, [C.c_int, C.c_int64, C.c_int64, _i32p, _i32p, C.c_int64, C.c_int, C.c_int,
+                                      _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "opmb200_partition_simple": (C.c_int, [C.c_int32, C.c_int32, _i32p]),
     "opmb200_localize": (C.c_int, [C.c_int64, _i32p, _i32p, _i32p, C.c_int32, C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64), _vp, _vp, _vp, _vp]),
@@ -163,9 +166,13 @@ def ptr(a) -> C.c_void_p:
     if isinstance(a, np.ndarray):
         if not a.flags.c_contiguous:
             raise ValueError("array must be C-contiguous")
+        if a.dtype != np.float64:
+            raise TypeError(f"the C ABI takes double*: got a {a.dtype} array")
         return C.c_void_p(a.ctypes.data)
     if hasattr(a, "data_ptr"):  # torch tensor
         if not a.is_contiguous():
             raise ValueError("tensor must be contiguous")
+        if "float64" not in str(a.dtype):
+            raise TypeError(f"the C ABI takes double*: got a {a.dtype} tensor")
         return C.c_void_p(a.data_ptr())
     raise TypeError(f"cannot take the address of {type(a)}")

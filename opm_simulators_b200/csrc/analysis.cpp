@@ -111,19 +111,31 @@ int32_t contiguous_chunks(int64_t n, int64_t n_interior, const std::vector<int32
 }
 
 // chunk ids of TJ x TK tiles of grid lines on a box grid in natural order (nx cells per line, ny
-// lines per plane): 32 lines per chunk, one per lane, so that the j-1 AND the k-1 neighbour of most
-// rows are served by the chunk's own ring; tiles are numbered plane-band by plane-band.  Ghost
-// rows (>= n_interior) get contiguous chunks behind the tiles.  The caller validates the result
-// (chunk_order_valid): the pattern need not be a clean 7-point stencil.
+// lines per plane): one line per row of a step, so that the j-1 AND the k-1 neighbour of most rows
+// are served by the chunk's own ring.  Tiles are numbered by the time the wavefront reaches them
+// (TJ*tj + TK*tk: the step at which tile (tj, tk) can start), so that the tiles the in-order ticket
+// keeps resident are the ones the front is working on.  Ghost rows (>= n_interior) get contiguous
+// chunks behind the tiles.  The caller validates the result (chunk_order_valid): the pattern need
+// not be a clean 7-point stencil.
 int32_t tile_chunks(int64_t n, int64_t n_interior, int64_t nx, int64_t ny, int TJ, int TK, std::vector<int32_t>& chunk_id)
 {
     chunk_id.resize(n);
     const int64_t nxy = nx * ny;
     const int64_t ntj = (ny + TJ - 1) / TJ;
+    const int64_t nz = n_interior > 0 ? (n_interior - 1) / nxy + 1 : 0;
+    const int64_t ntk = (nz + TK - 1) / TK;
+    std::vector<int64_t> order(ntj * ntk);
+    std::iota(order.begin(), order.end(), (int64_t)0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+        return TJ * (a % ntj) + TK * (a / ntj) < TJ * (b % ntj) + TK * (b / ntj);
+    });
+    std::vector<int32_t> rank(ntj * ntk, 0);
+    for (size_t r = 0; r < order.size(); ++r)
+        rank[order[r]] = (int32_t)r;
     int32_t nc = 0;
     for (int64_t i = 0; i < n_interior; ++i) {
         const int64_t k = i / nxy, j = (i % nxy) / nx;
-        chunk_id[i] = (int32_t)((k / TK) * ntj + j / TJ);
+        chunk_id[i] = rank[(k / TK) * ntj + j / TJ];
         nc = std::max(nc, chunk_id[i] + 1);
     }
     for (int64_t i = n_interior; i < n; ++i)
@@ -149,7 +161,7 @@ bool chunk_order_valid(int64_t n, const int32_t* col, const std::vector<int32_t>
 
 template <class RowBegin, class RowEnd>
 void plan_chunks(int64_t n, const int32_t* col, const std::vector<int32_t>& chunk_id, int32_t n_chunks,
-                 RowBegin row_begin, RowEnd row_end, double t_ext, ChunkPlan& P)
+                 RowBegin row_begin, RowEnd row_end, double t_ext, int R, ChunkPlan& P)
 {
     P.n_chunks = n_chunks;
     auto chunk_of = [&](int64_t i) { return (int64_t)chunk_id[i]; };
@@ -209,7 +221,7 @@ void plan_chunks(int64_t n, const int32_t* col, const std::vector<int32_t>& chun
                     start = std::max(start, done[P.grp[c]] + t_ext);
             }
         }
-        const double cost = (width[g] + kSlice - 1) / kSlice;
+        const double cost = (width[g] + R - 1) / R;
         done[g] = start + cost;
         total += cost;
         tmax = std::max(tmax, done[g]);
@@ -293,18 +305,29 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
         }
     }
     L.symmetric = symmetric;
-    L.schedule_mode = schedule_mode;
+    // the tile walkers stage at most 4 dependency blocks per row and direction; wider rows (NNC- or
+    // well-like) keep the level schedule
+    int max_wl = 0, max_wu = 0;
+    for (int64_t i = 0; i < n_interior; ++i) {
+        max_wl = std::max<int>(max_wl, diag[i] - rowptr[i]);
+        max_wu = std::max<int>(max_wu, rowptr[i + 1] - 1 - diag[i]);
+    }
+    const bool auto_mode = schedule_mode == 2;
+    const int max_slots = b >= 3 ? 4 : 3; // instantiated tile walkers (solver.cu, DISPATCH_BS)
+    if (schedule_mode != 0 && (max_wl > max_slots || max_wu > max_slots || n >= (int64_t)kTwExt))
+        schedule_mode = 0;
+    const int R = kTwWarps * (32 / b); // rows of one CTA step
     int32_t nlev = 0;
     for (int64_t i = 0; i < n; ++i)
         nlev = std::max(nlev, lev[i] + 1);
     if (n == 0)
         nlev = 0;
     std::vector<int32_t> grp_chunk;
-    if (schedule_mode == 1 && n > 0) {
+    if (schedule_mode != 0 && n > 0) {
         // chunk size: given, or the candidate with the shortest estimated sweep (critical path of
-        // the chunk dataflow, or total work over the ~1184 chunks a B200 keeps resident)
+        // the chunk dataflow, or total work over the ~296 tile walkers a B200 keeps resident)
         ChunkPlan best;
-        const double t_ext = 4.0, resident = 1184.0;
+        const double t_ext = 6.0, resident = 296.0;
         std::vector<int64_t> cands;
         int64_t line = 0, plane = 0; // nx and nx*ny of a box grid in natural order (0: not recognised)
         if (chunk_rows > 0) {
@@ -312,7 +335,7 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
         }
         if (chunk_rows <= 0) {
             // "line length" of the ordering = the most frequent lower offset larger than 1 (nx on a
-            // box grid): chunks of 32 lines fill the 32 lanes of a slice best
+            // box grid)
             std::vector<int64_t> offs;
             const int64_t stride = std::max<int64_t>(1, n_interior / 200000);
             for (int64_t r = 0; r < n_interior; r += stride)
@@ -344,49 +367,62 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
             }
             if (bestp * 4 < bestc)
                 plane = 0;
-            for (int64_t R : {(int64_t)1024, (int64_t)2048, (int64_t)4096, (int64_t)8192, 16 * line, 32 * line, 64 * line})
-                if (chunk_rows == 0 && R >= 256 && R <= 65536 && std::find(cands.begin(), cands.end(), R) == cands.end())
-                    cands.push_back(R);
+            for (int64_t C : {(int64_t)1024, (int64_t)2048, (int64_t)4096, (int64_t)8192, (R / 2) * line, R * line, 2 * R * line})
+                if (chunk_rows == 0 && !auto_mode && C >= 256 && C <= 65536 && std::find(cands.begin(), cands.end(), C) == cands.end())
+                    cands.push_back(C);
         }
         double best_cost = -1;
-        auto consider = [&](const std::vector<int32_t>& chunk_id, int32_t nc, int64_t R) {
+        auto consider = [&](const std::vector<int32_t>& chunk_id, int32_t nc, int64_t tag) {
             ChunkPlan P;
-            plan_chunks(n, col, chunk_id, nc, row_begin, row_end, t_ext, P);
-            const double padding = P.total_steps * kSlice / (double)std::max<int64_t>(n, 1);
+            plan_chunks(n, col, chunk_id, nc, row_begin, row_end, t_ext, R, P);
+            const double padding = P.total_steps * R / (double)std::max<int64_t>(n, 1);
             const double cost = std::max(P.est_steps, P.total_steps / resident) + 200.0 * std::max(0.0, padding - 1.6);
             if (best_cost < 0 || cost < best_cost) {
                 best_cost = cost;
                 best = std::move(P);
-                L.chunk_rows = (int)R;
+                L.chunk_rows = (int)tag;
             }
         };
         std::vector<int32_t> chunk_id;
-        for (int64_t R : cands) {
-            const int32_t nc = contiguous_chunks(n, n_interior, lev, R, chunk_id);
-            consider(chunk_id, nc, R);
+        for (int64_t C : cands) {
+            const int32_t nc = contiguous_chunks(n, n_interior, lev, C, chunk_id);
+            consider(chunk_id, nc, C);
         }
-        // box grids: tiles of 32 grid lines (chunk_rows reports -(TJ*100 + TK); a negative request
-        // forces that tile shape)
+        // box grids: tiles of R grid lines, one line per row of a step (chunk_rows reports
+        // -(TJ*100 + TK); a negative request forces that tile shape)
+        bool tiled = false;
         if (chunk_rows <= 0 && line > 1 && plane > line && plane % line == 0) {
-            for (int TK : {2, 4, 8}) {
-                const int TJ = 32 / TK;
+            for (int TK = 1; TK <= R; ++TK) {
+                if (R % TK)
+                    continue;
+                const int TJ = R / TK;
                 if (chunk_rows < 0 && chunk_rows != -(TJ * 100 + TK))
                     continue;
+                if (chunk_rows == 0 && (TJ < 2 || TK < 2))
+                    continue;
                 const int32_t nc = tile_chunks(n, n_interior, line, plane / line, TJ, TK, chunk_id);
-                if (chunk_order_valid(n, col, chunk_id, row_begin, row_end))
+                if (chunk_order_valid(n, col, chunk_id, row_begin, row_end)) {
                     consider(chunk_id, nc, -(TJ * 100 + TK));
+                    tiled = true;
+                }
             }
         }
-        if (best_cost < 0) { // a forced tile shape that the pattern does not admit: contiguous chunks
+        if (auto_mode && !tiled) {
+            schedule_mode = 0; // "auto": only box grids leave the level schedule
+        } else if (best_cost < 0) { // a forced tile shape that the pattern does not admit: contiguous chunks
             const int32_t nc = contiguous_chunks(n, n_interior, lev, 2048, chunk_id);
             consider(chunk_id, nc, 2048);
         }
-        lev = best.grp; // group id replaces the level from here on
-        nlev = best.n_groups;
-        grp_chunk = best.grp_chunk;
-        L.n_chunks = best.n_chunks;
-        L.est_steps = best.est_steps;
+        if (schedule_mode != 0) {
+            schedule_mode = 1;
+            lev = best.grp; // group id replaces the level from here on
+            nlev = best.n_groups;
+            grp_chunk = best.grp_chunk;
+            L.n_chunks = best.n_chunks;
+            L.est_steps = best.est_steps;
+        }
     }
+    L.schedule_mode = schedule_mode;
     L.n_levels = nlev;
     L.level_q0.assign(nlev + 1, 0);
     for (int64_t i = 0; i < n; ++i)
@@ -402,6 +438,76 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
             L.r2n[q] = (int32_t)i;
             L.n2r[i] = q;
         }
+    }
+
+    // ---- mode 1: cut the groups into the steps of the tile walkers ------------------------------
+    // A step holds <= R rows (one CTA step) and <= kTwMaxExt dependencies per direction that the
+    // chunk's ring does not serve (one per lane of a poll warp).  A dependency is served by the ring
+    // iff it lies in the same chunk at most `window` positions away: the ring holds tw_ring
+    // positions and a step overwrites at most R of them, so everything up to tw_ring - R positions
+    // before the first row of a step (behind its last row, upper sweep) is intact.
+    int tw_window = 0;
+    if (schedule_mode == 1) {
+        L.tw_rows = R;
+        L.tw_ring = 256;
+        while (L.tw_ring < 4 * R)
+            L.tw_ring *= 2;
+        L.tw_slots[0] = std::max(3, max_wl);
+        L.tw_slots[1] = std::max(3, max_wu);
+        tw_window = L.tw_ring - 2 * R;
+        auto n_ext = [&](int64_t i, bool upper) {
+            if (i >= n_interior)
+                return 0;
+            int cnt = 0;
+            const int32_t q = L.n2r[i];
+            for (int64_t k = upper ? diag[i] + 1 : rowptr[i]; k < (upper ? rowptr[i + 1] : diag[i]); ++k) {
+                const int32_t c = col[k], pp = L.n2r[c];
+                if (!(grp_chunk[lev[c]] == grp_chunk[lev[i]] && (upper ? pp - q : q - pp) <= tw_window))
+                    ++cnt;
+            }
+            return cnt;
+        };
+        std::vector<int32_t> step_chunk;
+        L.step_q0.clear();
+        for (int32_t g = 0; g < nlev; ++g) {
+            int32_t q = L.level_q0[g];
+            while (q < L.level_q0[g + 1]) {
+                L.step_q0.push_back(q);
+                step_chunk.push_back(grp_chunk[g]);
+                int count = 0, elo = 0, eup = 0;
+                while (q < L.level_q0[g + 1] && count < R) {
+                    const int64_t i = L.r2n[q];
+                    const int a = n_ext(i, false), u = n_ext(i, true);
+                    if (count > 0 && (elo + a > kTwMaxExt || eup + u > kTwMaxExt))
+                        break;
+                    ++count;
+                    elo += a;
+                    eup += u;
+                    ++q;
+                }
+            }
+        }
+        L.n_steps = (int)step_chunk.size();
+        L.step_q0.push_back((int32_t)n);
+        L.chunk_step0.assign(L.n_chunks + 1, 0);
+        for (int32_t st = 0; st < L.n_steps; ++st) // steps are ordered by chunk
+            L.chunk_step0[step_chunk[st] + 1] = st + 1;
+        for (int32_t c = 0; c < L.n_chunks; ++c)
+            L.chunk_step0[c + 1] = std::max(L.chunk_step0[c + 1], L.chunk_step0[c]);
+        L.step_flags.assign(L.n_steps, 0);
+        for (int32_t st = 0; st < L.n_steps; ++st)
+            if (L.r2n[L.step_q0[st]] >= n_interior)
+                L.step_flags[st] = 1;
+        // the chunk of a ROW is needed again for the dependency codes below
+        std::vector<int32_t> row_chunk(n);
+        for (int64_t i = 0; i < n; ++i)
+            row_chunk[i] = grp_chunk[lev[i]];
+        lev.swap(row_chunk); // lev[i] = chunk of row i from here on
+        // steps replace the groups: no slice crosses a step
+        grp_chunk = step_chunk;
+        nlev = L.n_steps;
+        L.n_levels = nlev;
+        L.level_q0 = L.step_q0;
     }
 
     // ---- slices --------------------------------------------------------------------------------
@@ -485,32 +591,44 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
         }
     }
 
-    // ---- chunk sweeps: which dependencies the shared-memory ring of a chunk serves ------------------
-    L.sweep_col.clear();
+    // ---- mode 1: dependency codes, external lists and block slots of every step -------------------
+    for (int d = 0; d < 2; ++d) {
+        L.tw_code[d].clear();
+        L.tw_ext[d].clear();
+        L.tw_next[d].clear();
+        L.tw_slot[d].clear();
+    }
     if (schedule_mode == 1) {
-        constexpr int32_t kRingValid = 96, kRingFlag = 1 << 30; // kernels.cuh
-        if (n >= (int64_t)kRingFlag) {
-            err = "matrix too large for the chunk schedule";
-            return OPMB200_INVALID_ARGUMENT;
+        const int RP = L.tw_rp();
+        for (int d = 0; d < 2; ++d) {
+            const int S = L.tw_slots[d];
+            L.tw_code[d].assign((size_t)L.n_steps * S * RP, -1);
+            L.tw_ext[d].assign((size_t)L.n_steps * kTwMaxExt, -1);
+            L.tw_next[d].assign(L.n_steps, 0);
+            L.tw_slot[d].assign((size_t)S * n, -1);
         }
-        L.sweep_col = L.slot_col;
-        for (int32_t c = 0; c < L.n_chunks; ++c) {
-            const int32_t q_lo = L.slice_q0[L.chunk_slice0[c]], q_hi = L.slice_q0[L.chunk_slice0[c + 1]];
-            for (int s = L.chunk_slice0[c]; s < L.chunk_slice0[c + 1]; ++s) {
-                const int32_t q0 = L.slice_q0[s], q1 = L.slice_q0[s + 1];
-                const int64_t base = L.slice_base[s];
-                const int wl = L.slice_wl[s], wu = L.slice_wu[s];
-                for (int sr = 0; sr < wl + 1 + wu; ++sr) {
-                    if (sr == wl)
-                        continue;
-                    for (int lane = 0; lane < q1 - q0; ++lane) {
-                        int32_t& p = L.sweep_col[(base + sr) * kSlice + lane];
-                        if (p < 0)
-                            continue;
-                        const bool ring = sr < wl ? (p < q0 && p >= q0 - kRingValid && p >= q_lo)
-                                                  : (p >= q1 && p < q1 + kRingValid && p < q_hi);
-                        if (ring)
-                            p |= kRingFlag;
+        for (int32_t st = 0; st < L.n_steps; ++st) {
+            for (int32_t q = L.step_q0[st]; q < L.step_q0[st + 1]; ++q) {
+                const int rho = q - L.step_q0[st];
+                const int64_t i = L.r2n[q];
+                if (i >= n_interior)
+                    continue; // ghost rows: identity
+                for (int d = 0; d < 2; ++d) {
+                    const int S = L.tw_slots[d];
+                    const int w = d ? rowptr[i + 1] - 1 - diag[i] : diag[i] - rowptr[i];
+                    for (int k = 0; k < w; ++k) { // lower: ascending column; upper: descending (slot order of the SELL layout)
+                        const int64_t e = d ? (int64_t)rowptr[i + 1] - 1 - k : (int64_t)rowptr[i] + k;
+                        const int32_t c = col[e], pp = L.n2r[c];
+                        int32_t code;
+                        if (lev[c] == lev[i] && (d ? pp - q : q - pp) <= tw_window) {
+                            code = kTwRing | (pp & (L.tw_ring - 1));
+                        } else {
+                            const int l = L.tw_next[d][st]++;
+                            L.tw_ext[d][(size_t)st * kTwMaxExt + l] = pp;
+                            code = kTwExt | l;
+                        }
+                        L.tw_code[d][((size_t)st * S + k) * RP + rho] = code;
+                        L.tw_slot[d][(size_t)k * n + q] = slot_of_native[e];
                     }
                 }
             }

@@ -832,7 +832,6 @@ struct FactorArgs {
     const int* trip_dst;
     const int* row_static;  // ILU0: the row's U blocks are never modified (by position)
     double* dinv;           // [n][b*b] by position
-    double* dinv_s;         // the same in slice layout [slice][b*b][32] (what the chunk sweeps stage)
     double* dinv_rec;       // Dinv as dependency records [n][b][Rec<b>::W] (sentinel-armed before the launch)
     int* row_flag;          // [n]
     int epoch;
@@ -937,7 +936,6 @@ __global__ void __launch_bounds__(kCtaThreads) dilu_factor_kernel(FactorArgs a)
             for (int e = 0; e < BB; ++e) {
                 D[e] = guard(D[e]);
                 a.dinv[(size_t)q * BB + e] = D[e];
-                a.dinv_s[((size_t)S * BB + e) * 32 + lane] = D[e];
             }
 #pragma unroll
             for (int r = 0; r < B; ++r) {
@@ -1080,8 +1078,7 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
                 for (int e = 0; e < BB; ++e) {
                     a.F[elem_index<BB>(m.base + m.wl, lane, e)] = D[e];
                     a.dinv[(size_t)q * BB + e] = D[e];
-                    a.dinv_s[((size_t)S * BB + e) * 32 + lane] = D[e];
-                }
+                    }
                 __threadfence(); // rows on the general path wait for the flag and read F and dinv
                 st_relaxed(a.row_flag + q, a.epoch);
                 goto row_done;
@@ -1133,7 +1130,6 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
                 D[e] = guard(D[e]);
                 a.F[elem_index<BB>(m.base + m.wl, lane, e)] = D[e];
                 a.dinv[(size_t)q * BB + e] = D[e];
-                a.dinv_s[((size_t)S * BB + e) * 32 + lane] = D[e];
             }
             // 3. publish: release fence, then the flag and the Dinv records the fast rows wait for
             __threadfence();
@@ -1381,93 +1377,8 @@ __global__ void __launch_bounds__(kCtaThreads, B <= 3 ? 2 : 1) sweep_kernel(Swee
 }
 
 // -------------------------------------------------------------------------------------------------
-// chunked-wavefront sweeps (schedule mode "chunks")
-//
-// A producer->consumer hop through the L2 costs 500-1000+ cycles, a hop that stays inside a warp
-// ~100.  Here ONE COMPUTE WARP walks ONE CHUNK (a contiguous run of rows of the natural ordering,
-// its rows ordered by chunk-local level) step after step (step = one 32-row slice):
-//   * dependencies on rows of the same chunk are served from a shared-memory ring of the last 96
-//     results (the analysis marks those slots with kRingFlag in `sweep_col`); only dependencies
-//     that cross a chunk boundary are sampled in the L2 (dependency records + sentinel, as in
-//     sweep_kernel), and they are sampled one step ahead, so a producer that is already done
-//     costs no round trip;
-//   * every compute warp has a LOADER warp (one lane of it works): each step's matrix data (header,
-//     column positions, block values, Dinv) is ONE contiguous record of a per-sweep stream
-//     (cw_stream_fill_kernel), so the loader's step is: wait on the stage's "empty" mbarrier,
-//     arm its "full" mbarrier, issue one TMA bulk copy (cp.async.bulk -> UBLKCP) from a pointer
-//     it increments.  A loader that has to compute addresses or issue several copies per step
-//     (~200 instructions on a lone thread ~ 1000 cycles) is slower than the compute warp and
-//     becomes the step time -- measured.  The compute warp executes no address arithmetic and no
-//     TMA issue: its step is ~one basic block of LDS + DFMA + 2-4 stores.
+// shared-memory / mbarrier / TMA helpers of the tile walkers (tile_kernels.cuh)
 // -------------------------------------------------------------------------------------------------
-constexpr int kCwWarps = 4;        // compute warps per CTA (and as many loader warps)
-constexpr int kRing = 128;         // ring positions per compute warp
-constexpr int kRingValid = 96;     // how far back the ring may be read (kRing - 32: no aliasing with the step's writes)
-constexpr int kRingFlag = 1 << 30; // sweep_col: the dependency is served by the ring
-constexpr int kCwHasExt = 1 << 16; // step header, width word: some row of the step has a dependency outside the ring
-
-template <int B>
-struct CwSmem {
-    static constexpr int BB = B * B;
-    static constexpr int kStages = (B <= 3) ? 5 : 3;
-    static constexpr int kHdrOff = 0;                         // int4 {q0, count, width | kCwHasExt, first slot row}
-    static constexpr int kColOff = 128;                       // kPrefetch x 32 column positions (+ kRingFlag)
-    // block values element-major like the SELL slots: element e of lane l at (e*32 + l)*8
-    // (a pair layout read with LDS.128 was measured: fewer instructions, same step time)
-    static constexpr int kSlotBytes = BB * 32 * 8;
-    static constexpr int kBlkOff = kColOff + kPrefetch * 128; // kPrefetch block slots
-    static constexpr int kBlkBytes = kPrefetch * kSlotBytes;
-    static constexpr int kDinvOff = kBlkOff + kBlkBytes;
-    static constexpr int kDinvBytes = kSlotBytes;
-    static constexpr int kStageBytes = kDinvOff + kDinvBytes; // multiple of 128
-    static constexpr int kRingOff = kStages * kStageBytes;
-    static constexpr int kRingBytes = kRing * B * 8;
-    static constexpr int kBarOff = kRingOff + kRingBytes; // kStages "full" mbarriers, then the progress counter
-    static constexpr int kProgressOff = kBarOff + 64;
-    static constexpr int kWarpBytes = kBarOff + 128;
-    static constexpr int kCtaBytes = kCwWarps * kWarpBytes;
-};
-
-// One step record of a sweep stream = exactly what a stage receives: header, column positions,
-// kPrefetch slot rows of block values (zero beyond the width) and, except for the ILU0 lower sweep,
-// Dinv.  The records of a chunk are contiguous in walking order (lower: slice order; upper: reverse),
-// so the loader issues ONE bulk copy per step from a pointer it merely increments.
-template <int B>
-__host__ __device__ constexpr int cw_record_bytes(bool with_dinv)
-{
-    return CwSmem<B>::kDinvOff + (with_dinv ? CwSmem<B>::kDinvBytes : 0);
-}
-
-struct CwArgs {
-    int nchunks;
-    const int* chunk_slice0; // [nchunks+1]
-    const SliceMeta* slices;
-    const int* slot_col;  // plain column positions (rows wider than kPrefetch)
-    const unsigned char* stream; // this sweep's step records (cw_record_bytes each), in walking order
-    int nslices;
-    const double* M;      // SELL values, only for rows wider than kPrefetch
-    const double* d;
-    double* tmp;   // dependency records of the lower sweep's result y
-    double* vpoll; // dependency records of the upper sweep's result
-    double* v;
-    const int* r2n;
-    int64_t n, n_interior;
-    int ghost_zero;
-    int prefetch; // L2 look-ahead of the loader warps, in steps (0..32)
-    int debug;    // OPMB200_PROFILE builds only: timing experiments that switch parts of the step off (wrong results)
-    Ticket ticket;
-    Scalars* sc;
-    int check_done;
-};
-
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes)
-{
-    // cp.async.bulk.prefetch.L2 (SASS: UBLKPF.L2); address and size rounded to 16 bytes
-    const unsigned long long a = (unsigned long long)p;
-    const unsigned long long a0 = a & ~15ull;
-    const unsigned sz = (unsigned)(((a + bytes + 15ull) & ~15ull) - a0);
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(sz) : "memory");
-}
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
 {
@@ -1500,532 +1411,6 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, unsigned
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
-}
-// strong record load WITHOUT a compiler memory barrier: the look-ahead samples may be scheduled
-// freely among the shared-memory loads of the running step (they touch other rows' records only)
-template <int B>
-__device__ __forceinline__ void rec_load_ahead(const double* base, size_t q, double (&x)[B])
-{
-    const double* p = base + q * Rec<B>::W;
-    if constexpr (Rec<B>::W == 2) {
-        double w0, w1;
-        asm volatile("ld.relaxed.gpu.global.v2.f64 {%0,%1}, [%2];" : "=d"(w0), "=d"(w1) : "l"(p));
-        x[0] = w0;
-        if constexpr (B == 2)
-            x[1] = w1;
-    } else {
-        double w0, w1, w2, w3;
-        asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(w0), "=d"(w1), "=d"(w2), "=d"(w3) : "l"(p));
-        x[0] = w0;
-        x[1] = w1;
-        x[2] = w2;
-        if constexpr (B == 4)
-            x[3] = w3;
-    }
-}
-// the BB values of lane `lane` in a block slot of a stage (shared memory)
-template <int BB>
-__device__ __forceinline__ void cw_load_slot(const unsigned char* slot, int lane, double (&v)[BB])
-{
-    const double* p = reinterpret_cast<const double*>(slot) + lane;
-#pragma unroll
-    for (int e = 0; e < BB; ++e)
-        v[e] = p[e * 32];
-}
-
-__device__ __forceinline__ bool cw_is_ring(int c) { return ((unsigned)c >> 30) == 1u; }
-__device__ __forceinline__ bool cw_is_ext(int c) { return ((unsigned)c >> 30) == 0u; }
-
-#ifdef OPMB200_PROFILE
-#define CW_DBG(bit) (a.debug & (bit))
-#else
-#define CW_DBG(bit) false
-#endif
-#ifdef OPMB200_PROFILE
-// in-kernel phase profile of the compute warps (lane 0): cycles per phase summed over all steps
-__device__ unsigned long long g_prof[16];
-__device__ unsigned long long g_chunk_t[3 * 4096]; // per chunk: resident, first step ready, done (globaltimer ns)
-__device__ __forceinline__ unsigned long long gtime()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-#define PROF_CHUNK(c, k)                                                                                               \
-    do {                                                                                                               \
-        if (lane == 0 && (c) < 4096)                                                                                   \
-            g_chunk_t[3 * (c) + (k)] = gtime();                                                                        \
-    } while (0)
-#define PROF_DECL long long tprev__ = clock64(); unsigned long long pacc__[8] = {0, 0, 0, 0, 0, 0, 0, 0}
-#define PROF_MARK(i)                                                                                                   \
-    do {                                                                                                               \
-        const long long now__ = clock64();                                                                             \
-        pacc__[i] += (unsigned long long)(now__ - tprev__);                                                            \
-        tprev__ = now__;                                                                                               \
-    } while (0)
-#define PROF_COUNT(i)                                                                                                  \
-    do {                                                                                                               \
-        if (lane == 0)                                                                                                 \
-            atomicAdd(&g_prof[i], 1ull);                                                                               \
-    } while (0)
-#define PROF_FLUSH(nsteps)                                                                                             \
-    do {                                                                                                               \
-        if (lane == 0) {                                                                                               \
-            for (int i__ = 0; i__ < 8; ++i__)                                                                          \
-                atomicAdd(&g_prof[i__], pacc__[i__]);                                                                  \
-            atomicAdd(&g_prof[8], (unsigned long long)(nsteps));                                                       \
-            atomicAdd(&g_prof[9], 1ull);                                                                               \
-        }                                                                                                              \
-    } while (0)
-#else
-#define PROF_CHUNK(c, k)
-#define PROF_DECL
-#define PROF_COUNT(i)
-#define PROF_MARK(i)
-#define PROF_FLUSH(nsteps)
-#endif
-
-// what a compute warp holds about a step before it runs it
-template <int B>
-struct CwStep {
-    int4 hdr;                 // q0, count, width, first slot row
-    int cj[kPrefetch];        // staged column positions (-1: none)
-    double ext[kPrefetch][B]; // sampled records of the dependencies outside the ring (0 elsewhere)
-    double in[B];             // the row's own input: d_i (lower), y_i (upper)
-};
-
-// ---- loader warp (one lane) -----------------------------------------------------------------------
-template <int B, bool ILU0, bool UPPER>
-__device__ __forceinline__ void cw_loader(const CwArgs& a, unsigned char* wbase, int s0, int s1)
-{
-    using SM = CwSmem<B>;
-    constexpr int NS = SM::kStages;
-    constexpr unsigned kRec = (unsigned)cw_record_bytes<B>(!(ILU0 && !UPPER));
-    const int ns = s1 - s0;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(wbase + SM::kBarOff);
-    volatile int* progress = reinterpret_cast<volatile int*>(wbase + SM::kProgressOff); // steps the compute warp has finished
-    const unsigned char* src = a.stream + (size_t)(UPPER ? a.nslices - s1 : s0) * kRec;
-    const int PF = a.prefetch;
-    int st = 0;
-    int done = 0;
-    for (int t = 0; t < ns; ++t) {
-        // stage st is free once step t - NS is finished.  A plain shared-memory counter, not an
-        // "empty" mbarrier: an arrive per step on the compute warp's side costs it ~200 cycles
-        // (scripts/microbench_mbar.cu), a store costs nothing.  The compute warp's last reads of a
-        // stage feed the values it stores to its ring before it bumps the counter, so the copy
-        // issued here cannot overtake them.
-        while (done < t + 1 - NS) {
-            done = *progress;
-            if (done < t + 1 - NS)
-                __nanosleep(32);
-        }
-        mbar_expect_tx(full + st, CW_DBG(8) ? 0u : kRec);
-        if (!CW_DBG(8))
-            tma_load_1d(wbase + (size_t)st * SM::kStageBytes, src, kRec, full + st);
-        if (PF > 0 && t >= NS && t + PF < ns)
-            l2_prefetch_bulk(src + (size_t)PF * kRec, kRec); // keeps pace with the compute warp
-        src += kRec;
-        if (++st == NS)
-            st = 0;
-    }
-}
-
-// ---- compute warp ---------------------------------------------------------------------------------
-// predicated strong record load / store: one instruction, no branch (x keeps its value when !p)
-template <int B>
-__device__ __forceinline__ void rec_load_ahead_if(bool p, const double* base, size_t q, double (&x)[B])
-{
-    const double* ptr = base + q * Rec<B>::W;
-    const unsigned pr = p ? 1u : 0u;
-    if constexpr (Rec<B>::W == 2) {
-        double w0 = x[0], w1 = (B == 2) ? x[B - 1] : 0.0;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.relaxed.gpu.global.v2.f64 {%0,%1}, [%2];\n\t}"
-                     : "+d"(w0), "+d"(w1)
-                     : "l"(ptr), "r"(pr));
-        x[0] = w0;
-        if constexpr (B == 2)
-            x[1] = w1;
-    } else {
-        double w0 = x[0], w1 = x[1], w2 = x[2], w3 = (B == 4) ? x[B - 1] : 0.0;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];\n\t}"
-                     : "+d"(w0), "+d"(w1), "+d"(w2), "+d"(w3)
-                     : "l"(ptr), "r"(pr));
-        x[0] = w0;
-        x[1] = w1;
-        x[2] = w2;
-        if constexpr (B == 4)
-            x[3] = w3;
-    }
-}
-template <int B>
-__device__ __forceinline__ void rec_store_strong_if(bool p, double* base, size_t q, const double (&x)[B])
-{
-    double* ptr = base + q * Rec<B>::W;
-    const unsigned pr = p ? 1u : 0u;
-    if constexpr (Rec<B>::W == 2) {
-        const double w1 = (B == 2) ? x[B - 1] : 0.0;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p st.relaxed.gpu.global.v2.f64 [%0], {%1,%2};\n\t}" ::"l"(ptr),
-                     "d"(x[0]), "d"(w1), "r"(pr)
-                     : "memory");
-    } else {
-        const double w3 = (B == 4) ? x[B - 1] : 0.0;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p st.relaxed.gpu.global.v4.f64 [%0], {%1,%2,%3,%4};\n\t}" ::"l"(ptr),
-                     "d"(x[0]), "d"(x[1]), "d"(x[2]), "d"(w3), "r"(pr)
-                     : "memory");
-    }
-}
-template <int B>
-__device__ __forceinline__ void rec_store_sentinel_if(bool p, double* base, size_t q)
-{
-    double x[B];
-#pragma unroll
-    for (int r = 0; r < B; ++r)
-        x[r] = __longlong_as_double((long long)kSentinelBits);
-    rec_store_strong_if<B>(p, base, q, x);
-}
-
-template <int B, bool ILU0, bool UPPER>
-__device__ __forceinline__ void cw_compute(const CwArgs& a, unsigned char* wbase, int s0, int s1, int lane, int chunk)
-{
-    using SM = CwSmem<B>;
-    constexpr int BB = B * B;
-    constexpr int NS = SM::kStages;
-    constexpr bool NEED_DINV = !(ILU0 && !UPPER);
-    const int ns = s1 - s0;
-    double* ring = reinterpret_cast<double*>(wbase + SM::kRingOff);
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(wbase + SM::kBarOff);
-    volatile int* progress = reinterpret_cast<volatile int*>(wbase + SM::kProgressOff);
-    double* out = UPPER ? a.vpoll : a.tmp;
-    const bool par = ILU0 && a.n_interior < a.n; // ghost rows exist (ParallelOverlappingILU0 leaves them alone)
-    const int q_lo = a.slices[s0].q0;
-    const int q_hi = a.slices[s1 - 1].q0 + a.slices[s1 - 1].count;
-    PROF_DECL;
-
-    // Everything about the step in stage `stg` that does not depend on the steps before it; no
-    // branches, so that it schedules into the running step's basic block.  Harmless on a stage
-    // that holds no step (zeros or an old record): it only issues loads.
-    auto look_ahead = [&](int stg, CwStep<B>& S) {
-        const unsigned char* sb = wbase + (size_t)stg * SM::kStageBytes;
-        S.hdr = *reinterpret_cast<const int4*>(sb + SM::kHdrOff);
-        const int* cols = reinterpret_cast<const int*>(sb + SM::kColOff);
-#pragma unroll
-        for (int s = 0; s < kPrefetch; ++s) {
-            const int c = cols[s * 32 + lane];
-            S.cj[s] = (s < (S.hdr.z & 0xffff)) ? c : -1;
-        }
-#pragma unroll
-        for (int s = 0; s < kPrefetch; ++s) {
-#pragma unroll
-            for (int r = 0; r < B; ++r)
-                S.ext[s][r] = 0.0;
-            const bool e = cw_is_ext(S.cj[s]) && !CW_DBG(2);
-            rec_load_ahead_if<B>(e, out, e ? (size_t)S.cj[s] : (size_t)0, S.ext[s]);
-        }
-        const bool act = lane < S.hdr.y;
-        const size_t q = act ? (size_t)(S.hdr.x + lane) : (size_t)0; // idle lanes load row 0: harmless, never stored
-        if (UPPER) {
-            rec_load_weak<B>(a.tmp, q, S.in);
-        } else {
-#pragma unroll
-            for (int r = 0; r < B; ++r)
-                S.in[r] = __ldcs(a.d + VIDX(a.n, q, r));
-            if (par) { // multi-rank ILU0 only
-                if (a.r2n[q] >= a.n_interior) {
-#pragma unroll
-                    for (int r = 0; r < B; ++r)
-                        S.in[r] = a.ghost_zero ? 0.0 : a.v[VIDX(a.n, q, r)];
-                }
-            }
-        }
-    };
-
-#ifndef CW_AHEAD
-#define CW_AHEAD 1
-#endif
-    constexpr int A = CW_AHEAD; // steps of look-ahead (dependency samples, own input, column positions)
-    int st0 = 0, st1 = A % NS, st2 = (A + 1) % NS; // stages of steps t, t+A, t+A+1
-    unsigned ph1 = (A / NS) & 1u, ph2 = ((A + 1) / NS) & 1u;
-
-    // one step: S is the running step (looked ahead one step ago), N receives the look-ahead of the
-    // next one; ok1 tells whether stage st1 (step t+1) had landed when it was tested a step ago.
-    // Returns the same for step t+2.
-    auto step = [&](int t, bool ok1, CwStep<B>& S, CwStep<B>& N) -> bool {
-        PROF_MARK(5);
-        // ---- rarely taken branches first, then ONE basic block ---------------------------------
-        if (!ok1)
-            mbar_wait(full + st1, ph1);
-        PROF_MARK(0);
-        // the next step's samples travel while this step waits for its own (sampling only after the
-        // wait costs the lower sweep 40 % on C3 -- measured).  One step of look-ahead: under load a
-        // sample takes ~1600 cycles, about two steps, so every step of every chunk but the lead ones
-        // stalls ~750 cycles on its own (valid) sample -- but sampling two steps ahead finds the
-        // record not written yet and ends in real polls (measured: 15 % slower), and issuing the
-        // step's strong stores behind the next samples instead of in front changes nothing.
-        const bool ok2 = (t + A + 1 < ns) ? mbar_try_wait(full + st2, ph2) : true; // consumed one step from now
-        look_ahead(st1, N);
-        PROF_MARK(1);
-        if (S.hdr.z & kCwHasExt) { // warp-uniform: the lead chunks of a wavefront never enter
-            unsigned pending = 0;
-#pragma unroll
-            for (int s = 0; s < kPrefetch; ++s)
-                if (cw_is_ext(S.cj[s]) && !rec_valid<B>(S.ext[s]))
-                    pending |= 1u << s;
-            if (__any_sync(0xffffffffu, pending != 0) && !CW_DBG(2)) {
-                // dependencies outside the ring that had not arrived when they were sampled one step
-                // ago.  At chunk start the producers may be a long way off: poll slowly.
-                int tries = 0;
-                do {
-                    PROF_COUNT(t == 0 ? 11 : 10);
-                    if (t == 0)
-                        __nanosleep(100);
-                    else if (++tries > 4)
-                        __nanosleep(20);
-#pragma unroll
-                    for (int s = 0; s < kPrefetch; ++s)
-                        if (pending & (1u << s)) {
-                            rec_load_strong<B>(out, (size_t)S.cj[s], S.ext[s]);
-                            if (rec_valid<B>(S.ext[s]))
-                                pending &= ~(1u << s);
-                        }
-                } while (__any_sync(0xffffffffu, pending != 0));
-            }
-        }
-        PROF_MARK(t == 0 ? 7 : 2);
-        if (t == 0)
-            PROF_CHUNK(chunk, 1);
-        const int q = S.hdr.x + lane;
-        const bool active = lane < S.hdr.y;
-        double extra[B]; // rows wider than the staged window (NNC / well rows): the rest, from memory
-#pragma unroll
-        for (int r = 0; r < B; ++r)
-            extra[r] = 0.0;
-        if ((S.hdr.z & 0xffff) > kPrefetch) {
-            if (active) {
-                const int sr0 = S.hdr.w;
-                for (int s = kPrefetch; s < (S.hdr.z & 0xffff); ++s) {
-                    const int cc = __ldg(a.slot_col + (size_t)(sr0 + s) * 32 + lane);
-                    if (cc < 0)
-                        continue;
-                    double bl[BB], xs[B];
-#pragma unroll
-                    for (int e = 0; e < BB; ++e)
-                        bl[e] = __ldcs(a.M + elem_index<BB>(sr0 + s, lane, e));
-                    const bool in_ring = UPPER ? (cc >= S.hdr.x + S.hdr.y && cc < S.hdr.x + S.hdr.y + kRingValid && cc < q_hi)
-                                               : (cc < S.hdr.x && cc >= S.hdr.x - kRingValid && cc >= q_lo);
-                    if (in_ring) {
-#pragma unroll
-                        for (int r = 0; r < B; ++r)
-                            xs[r] = ring[r * kRing + (cc & (kRing - 1))];
-                    } else {
-                        do {
-                            rec_load_strong<B>(out, (size_t)cc, xs);
-                        } while (!rec_valid<B>(xs));
-                    }
-                    blk_umv<B>(bl, xs, extra);
-                }
-            }
-            __syncwarp();
-        }
-
-        // ---- the step proper: one basic block ---------------------------------------------------
-        const unsigned char* sb = wbase + (size_t)st0 * SM::kStageBytes;
-        double rhs[B], yi[B], res[B];
-#pragma unroll
-        for (int r = 0; r < B; ++r) {
-            yi[r] = S.in[r];
-            rhs[r] = (UPPER && !ILU0) ? 0.0 : S.in[r];
-        }
-        if (!UPPER && !CW_DBG(1))
-            rec_store_sentinel_if<B>(active, a.vpoll, (size_t)(active ? q : 0)); // arm the upper sweep's records
-        // accumulate in slot order (the reference's summation order).  Straight-line code, no test
-        // of the width: a slot without a dependency has x = 0, and the stage rows beyond the width
-        // hold zeros (cw_stream_fill_kernel), so it adds exactly nothing.  All shared-memory loads
-        // of the step issue back to back ahead of the one dependent DFMA chain.
-        double di[BB];
-        if (NEED_DINV)
-            cw_load_slot<BB>(sb + SM::kDinvOff, lane, di);
-#pragma unroll
-        for (int s = 0; s < kPrefetch; ++s) {
-            double x[B], blk[BB];
-#pragma unroll
-            for (int r = 0; r < B; ++r)
-                x[r] = S.ext[s][r];
-            if (cw_is_ring(S.cj[s]) && !CW_DBG(4)) { // predicated loads, no branch
-#pragma unroll
-                for (int r = 0; r < B; ++r)
-                    x[r] = ring[r * kRing + (S.cj[s] & (kRing - 1))];
-            }
-            cw_load_slot<BB>(sb + SM::kBlkOff + s * SM::kSlotBytes, lane, blk);
-            if (CW_DBG(64)) {
-            } else if (UPPER && !ILU0)
-                blk_umv<B>(blk, x, rhs);
-            else
-                blk_mmv<B>(blk, x, rhs);
-        }
-#pragma unroll
-        for (int r = 0; r < B; ++r)
-            rhs[r] = (UPPER && !ILU0) ? rhs[r] + extra[r] : rhs[r] - extra[r];
-        if (NEED_DINV) {
-            if (!UPPER) {
-                blk_mv<B>(di, rhs, res); // DILU: y_i = Dinv_i (d_i - sum)
-            } else if (ILU0) {
-                blk_mv<B>(di, rhs, res); // v_i = Dinv_i (y_i - sum)
-                if (par) {
-                    if (active && a.r2n[q] >= a.n_interior) { // ghost rows keep y_i
-#pragma unroll
-                        for (int r = 0; r < B; ++r)
-                            res[r] = rhs[r];
-                    }
-                }
-            } else {
-                blk_mmv<B>(di, rhs, yi); // v_i = y_i - Dinv_i sum
-#pragma unroll
-                for (int r = 0; r < B; ++r)
-                    res[r] = yi[r];
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < B; ++r)
-                res[r] = rhs[r]; // ILU0 lower: L_ii = I
-        }
-#pragma unroll
-        for (int r = 0; r < B; ++r)
-            res[r] = guard(res[r]);
-        if (active && !CW_DBG(4)) {
-#pragma unroll
-            for (int r = 0; r < B; ++r)
-                ring[r * kRing + (q & (kRing - 1))] = res[r];
-        }
-        if (!CW_DBG(1)) {
-            rec_store_strong_if<B>(active, out, (size_t)(active ? q : 0), res);
-            if (UPPER) {
-                if (active) {
-#pragma unroll
-                    for (int r = 0; r < B; ++r)
-                        a.v[VIDX(a.n, q, r)] = res[r];
-                }
-                rec_store_sentinel_if<B>(active, a.tmp, (size_t)(active ? q : 0)); // re-arm for the next apply
-            }
-        }
-        PROF_MARK(3);
-        __syncwarp(); // ring writes visible to the warp; every lane is done with this stage
-        if (lane == 0)
-            *progress = t + 1; // releases the stage to the loader
-        PROF_MARK(4);
-        if (++st0 == NS)
-            st0 = 0;
-        st1 = st2;
-        ph1 = ph2;
-        if (++st2 == NS) {
-            st2 = 0;
-            ph2 ^= 1u;
-        }
-        return ok2;
-    };
-
-    CwStep<B> SA, SB;
-    PROF_CHUNK(chunk, 0);
-    mbar_wait(full + 0, 0u);
-    look_ahead(0, SA);
-#if CW_AHEAD == 2
-    CwStep<B> SC;
-    if (ns > 1)
-        mbar_wait(full + 1 % NS, (1 / NS) & 1u);
-    look_ahead(1 % NS, SB);
-#endif
-    bool ok1 = ns > A ? mbar_try_wait(full + st1, ph1) : true;
-    PROF_MARK(6);
-#if CW_AHEAD == 2
-    for (int t = 0; t < ns; t += 3) {
-        ok1 = step(t, ok1, SA, SC);
-        if (t + 1 < ns)
-            ok1 = step(t + 1, ok1, SB, SA);
-        if (t + 2 < ns)
-            ok1 = step(t + 2, ok1, SC, SB);
-    }
-#else
-    for (int t = 0; t < ns; t += 2) {
-        ok1 = step(t, ok1, SA, SB);
-        if (t + 1 < ns)
-            ok1 = step(t + 1, ok1, SB, SA);
-    }
-#endif
-    PROF_CHUNK(chunk, 2);
-    PROF_FLUSH(ns);
-}
-
-// fills the value part of the step records after a factorisation: block values from the SELL
-// slots (A for DILU, F for ILU0), Dinv from its slice layout.  One warp per slice and direction.
-template <int B>
-__global__ void __launch_bounds__(256) cw_stream_fill_kernel(int nslices, const SliceMeta* __restrict__ slices,
-                                                             const double* __restrict__ M, const double* __restrict__ dinv_s,
-                                                             unsigned char* __restrict__ lower, unsigned char* __restrict__ upper,
-                                                             int lower_has_dinv)
-{
-    using SM = CwSmem<B>;
-    constexpr int BB = B * B;
-    const int lane = threadIdx.x & 31;
-    const int gw = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
-    const int nw = (int)((gridDim.x * (size_t)blockDim.x) >> 5);
-    for (int job = gw; job < 2 * nslices; job += nw) {
-        const int s = job >> 1;
-        const bool up = job & 1;
-        const SliceMeta m = slices[s];
-        const int w = min(up ? m.wu : m.wl, kPrefetch);
-        const int sr0 = up ? m.base + m.wl + 1 : m.base;
-        const bool with_dinv = up || lower_has_dinv;
-        const size_t rec = (size_t)cw_record_bytes<B>(with_dinv);
-        unsigned char* dst = up ? upper + (size_t)(nslices - 1 - s) * rec : lower + (size_t)s * rec;
-        for (int k = 0; k < kPrefetch; ++k) {
-            double* slot = reinterpret_cast<double*>(dst + SM::kBlkOff + k * SM::kSlotBytes) + lane;
-#pragma unroll
-            for (int e = 0; e < BB; ++e)
-                slot[e * 32] = k < w ? __ldcs(M + elem_index<BB>(sr0 + k, lane, e)) : 0.0;
-        }
-        if (with_dinv) {
-            double* slot = reinterpret_cast<double*>(dst + SM::kDinvOff) + lane;
-#pragma unroll
-            for (int e = 0; e < BB; ++e)
-                slot[e * 32] = __ldcs(dinv_s + (size_t)s * 32 * BB + e * 32 + lane);
-        }
-    }
-}
-
-template <int B, bool ILU0, bool UPPER>
-__global__ void __launch_bounds__(kCwWarps * 64, 1) cw_sweep_kernel(CwArgs a)
-{
-    using SM = CwSmem<B>;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    const unsigned int ticket = take_ticket(a.ticket);
-    const bool skip = a.check_done && a.sc->done;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wi = (warp + ((warp >= kCwWarps && CW_DBG(32)) ? 1 : 0)) % kCwWarps; // compute warp wi and loader warp wi + kCwWarps share a chunk
-    unsigned char* wbase = smem_raw + (size_t)wi * SM::kWarpBytes;
-    // zero-filled stages: see the slot loop of cw_compute
-    for (int i = threadIdx.x; i < SM::kCtaBytes / 16; i += blockDim.x)
-        reinterpret_cast<int4*>(smem_raw)[i] = make_int4(0, 0, 0, 0);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes before the TMA writes
-    __syncthreads();
-    if (warp < kCwWarps && lane == 0) {
-        unsigned long long* bars = reinterpret_cast<unsigned long long*>(wbase + SM::kBarOff);
-        for (int i = 0; i < SM::kStages; ++i)
-            mbar_init(bars + i, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int cf = (int)ticket * kCwWarps + wi;
-    if (!skip && cf < a.nchunks) {
-        const int c = UPPER ? a.nchunks - 1 - cf : cf;
-        const int s0 = a.chunk_slice0[c], s1 = a.chunk_slice0[c + 1];
-        if (s1 > s0) {
-            if (warp >= kCwWarps) {
-                if (lane == 0)
-                    cw_loader<B, ILU0, UPPER>(a, wbase, s0, s1);
-            } else
-                cw_compute<B, ILU0, UPPER>(a, wbase, s0, s1, lane, c);
-        }
-    }
-    return_ticket(a.ticket);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -24,6 +24,9 @@
 namespace opmb200 {
 
 constexpr int kSlice = 32;
+constexpr int32_t kTwRing = 1 << 30, kTwExt = 1 << 29; // dependency codes of the tile walkers
+constexpr int kTwMaxExt = 32;                        // external dependencies per step (one per poll lane)
+constexpr int kTwWarps = 4;                          // compute warps of a tile walker
 
 struct Layout {
     int b = 0;
@@ -37,9 +40,12 @@ struct Layout {
     // earlier groups (lower sweep) / later groups (upper sweep).
     //   mode 0 "levels": group = level of pattern(A) U pattern(A^T) (== the reference level sets
     //                    when the pattern is structurally symmetric)
-    //   mode 1 "chunks": rows are cut into contiguous chunks of the natural ordering, group =
-    //                    (chunk, level inside the chunk); one warp walks one chunk, so only
-    //                    dependencies that cross a chunk boundary travel through the L2
+    //   mode 1 "tiles":  rows are cut into chunks (tiles of grid lines on a box grid, else contiguous
+    //                    runs of the natural ordering), group = (chunk, level inside the chunk), a
+    //                    group is cut into STEPS of <= tw_rows rows; one CTA walks one chunk step by
+    //                    step (tile_kernels.cuh), so only dependencies that cross a chunk boundary
+    //                    travel through the L2
+    //   mode 2 "auto":   request only: tiles when the pattern admits them, else levels
     int schedule_mode = 0;
     int chunk_rows = 0;
     int n_levels = 0;              // number of groups
@@ -62,9 +68,21 @@ struct Layout {
 
     std::vector<int32_t> slot_col; // [n_slot_rows*32]
     std::vector<int32_t> slot_src; // [n_slot_rows*32]
-    // mode 1: slot_col with bit 30 set where the dependency is served by the chunk's shared-memory
-    // ring (same chunk, at most kRingValid positions back / ahead), see cw_sweep_kernel
-    std::vector<int32_t> sweep_col; // [n_slot_rows*32]
+    // ---- mode 1: step tables of the tile walkers (tile_kernels.cuh) ------------------------------
+    int tw_rows = 0;                  // rows per CTA step: 4 warps x (32 / b) rows
+    int tw_ring = 0;                  // positions of a chunk's shared-memory ring (power of two)
+    int tw_slots[2] = {3, 3};         // dependency slots per row: lower, upper (3 or 4)
+    int n_steps = 0;
+    std::vector<int32_t> step_q0;     // [n_steps+1]
+    std::vector<int32_t> chunk_step0; // [n_chunks+1]
+    std::vector<int32_t> step_flags;  // [n_steps] bit 0: the step's rows are ghost rows
+    // per direction d (0 lower, 1 upper), by step s (NOT in walking order):
+    //   tw_code[d][(s*S + k)*RP + rho]: where row rho of the step finds dependency k:
+    //        -1 none | kTwRing + ring index | kTwExt + slot of the step's external list
+    //   tw_ext[d][s*32 + l]: position of external dependency l (-1 beyond tw_next[d][s])
+    //   tw_slot[d][k*n + q]: SELL slot of dependency block k of the row at position q (-1 none)
+    std::vector<int32_t> tw_code[2], tw_ext[2], tw_next[2], tw_slot[2];
+    int tw_rp() const { return (tw_rows + 3) & ~3; }
     // DILU: for every L slot (compact L numbering) the slot of the transposed block, or -1
     std::vector<int32_t> l_transpose; // [n_l_slot_rows*32]
     // ILU0: per compact L slot, the (source slot in row j, destination slot in row i) update pairs
@@ -83,7 +101,8 @@ int row_coloring(int64_t n, const int32_t* rowptr, const int32_t* col, int type,
                  int32_t* level_rows, int32_t* level_ptr);
 
 // Builds everything above.  Returns 0 or an opmb200_status (diagonal missing, bad arguments).
-// schedule_mode: 0 levels, 1 chunks; chunk_rows: rows per chunk (<= 0: chosen automatically)
+// schedule_mode: 0 levels, 1 tiles, 2 auto; chunk_rows: rows per chunk (> 0: contiguous chunks of that many
+// rows, 0: chosen automatically, -(TJ*100+TK): that tile shape)
 int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const int32_t* col, int64_t n_interior,
                  bool want_ilu0, int schedule_mode, int chunk_rows, Layout& L, std::string& err);
 

@@ -8,6 +8,7 @@
 #include "../../include/opmb200/property_tree.hpp"
 #include "kernels.cuh"
 #include "layout.hpp"
+#include "tile_kernels.cuh"
 
 #include <nccl.h>
 
@@ -118,10 +119,8 @@ struct opmb200_solver {
     int verbosity = 0;
     int op_repeats = 1;
     int throttle = 6;
-    int schedule = 0;   // 0 levels, 1 chunks
-    int chunk_rows = 0; // <= 0: automatic
-    int prefetch = 0;   // L2 look-ahead of the chunk sweeps' loader warps, in steps
-    int debug = 0;      // OPMB200_PROFILE builds: timing experiments (wrong results)
+    int schedule = 0;   // requested: 0 levels, 1 tiles, 2 auto (what was built: L.schedule_mode)
+    int chunk_rows = 0; // > 0 contiguous chunks, 0 automatic, < 0 a tile shape
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -130,9 +129,10 @@ struct opmb200_solver {
     int epoch = 0;
 
     DevBuf<SliceMeta> slices;
-    DevBuf<int> slot_col, slot_src, row_static, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag, chunk_slice0;
-    DevBuf<double> A, F, dinv, dinv_s, dinv_rec, vals_native;
-    DevBuf<unsigned char> stream_lo, stream_up; // chunk schedule: step records of the lower / upper sweep
+    DevBuf<int> slot_col, slot_src, row_static, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag;
+    DevBuf<int> chunk_step0, step_q0, tw_slot[2]; // schedule "tiles": step tables of the tile walkers
+    DevBuf<double> A, F, dinv, dinv_rec, vals_native;
+    DevBuf<unsigned char> tw_stream[2]; // schedule "tiles": step records of the lower / upper sweep
     DevBuf<double> vx, vr, vp, vv, vt, vy, vrt, vw, nat0, nat1;
     DevBuf<double> vtmp, vpoll; // dependency records of the sweeps, [n][2 or 4]
     DevBuf<double> partials, hist, sums, dot_out;
@@ -213,6 +213,17 @@ namespace {
     case 2: { constexpr int B = 2; __VA_ARGS__; } break;                                                               \
     case 3: { constexpr int B = 3; __VA_ARGS__; } break;                                                               \
     default: { constexpr int B = 4; __VA_ARGS__; } break;                                                              \
+    }
+
+// block size x dependency slots of the tile walkers (3 or 4; block sizes 1 and 2 only with 3)
+#define DISPATCH_BS(bsz, slots, ...)                                                                                   \
+    switch ((bsz) * 10 + (slots)) {                                                                                    \
+    case 13: { constexpr int B = 1, S = 3; __VA_ARGS__; } break;                                                       \
+    case 23: { constexpr int B = 2, S = 3; __VA_ARGS__; } break;                                                       \
+    case 33: { constexpr int B = 3, S = 3; __VA_ARGS__; } break;                                                       \
+    case 34: { constexpr int B = 3, S = 4; __VA_ARGS__; } break;                                                       \
+    case 43: { constexpr int B = 4, S = 3; __VA_ARGS__; } break;                                                       \
+    default: { constexpr int B = 4, S = 4; __VA_ARGS__; } break;                                                       \
     }
 
 int check_launch(opmb200_solver* s, const char* what)
@@ -365,40 +376,33 @@ SweepArgs sweep_args(opmb200_solver* s, const double* d, double* v, int ghost_ze
 
 int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
 {
-    if (s->schedule == 1) { // chunked wavefronts: one warp per chunk
-        CwArgs c;
+    if (s->L.schedule_mode == 1) { // tile walkers: one persistent CTA per resident slot, chunks by ticket
+        TwArgs c;
         c.nchunks = s->L.n_chunks;
-        c.chunk_slice0 = s->chunk_slice0.p;
-        c.slices = a.slices;
-        c.slot_col = a.slot_col;
-        c.stream = upper ? s->stream_up.p : s->stream_lo.p;
-        c.nslices = s->L.n_slices;
-        c.M = a.M;
+        c.chunk_step0 = s->chunk_step0.p;
+        c.nsteps = s->L.n_steps;
+        c.stream = s->tw_stream[upper ? 1 : 0].p;
         c.d = a.d;
         c.tmp = a.tmp;
         c.vpoll = a.vpoll;
         c.v = a.v;
-        c.r2n = a.r2n;
         c.n = a.n;
-        c.n_interior = a.n_interior;
         c.ghost_zero = a.ghost_zero;
-        c.prefetch = s->prefetch;
-        c.debug = s->debug;
         c.ticket = a.ticket;
         c.sc = a.sc;
         c.check_done = a.check_done;
-        const int cgrid = std::max(1, (s->L.n_chunks + kCwWarps - 1) / kCwWarps);
-        DISPATCH_B(s->b, {
-            constexpr int smem = CwSmem<B>::kCtaBytes;
-            if (s->prec == PREC_ILU0) {
-                if (upper) cw_sweep_kernel<B, true, true><<<cgrid, kCwWarps * 64, smem, s->stream>>>(c);
-                else cw_sweep_kernel<B, true, false><<<cgrid, kCwWarps * 64, smem, s->stream>>>(c);
+        const int cgrid = std::max(1, std::min(s->L.n_chunks, 2 * s->num_sms));
+        const bool ilu0 = s->prec == PREC_ILU0;
+        DISPATCH_BS(s->b, s->L.tw_slots[upper ? 1 : 0], {
+            if (ilu0) {
+                if (upper) tw_sweep_kernel<B, S, true, true><<<cgrid, kTwThreads, TwCfg<B, S, true>::kSmemBytes, s->stream>>>(c);
+                else tw_sweep_kernel<B, S, true, false><<<cgrid, kTwThreads, TwCfg<B, S, false>::kSmemBytes, s->stream>>>(c);
             } else {
-                if (upper) cw_sweep_kernel<B, false, true><<<cgrid, kCwWarps * 64, smem, s->stream>>>(c);
-                else cw_sweep_kernel<B, false, false><<<cgrid, kCwWarps * 64, smem, s->stream>>>(c);
+                if (upper) tw_sweep_kernel<B, S, false, true><<<cgrid, kTwThreads, TwCfg<B, S, true>::kSmemBytes, s->stream>>>(c);
+                else tw_sweep_kernel<B, S, false, false><<<cgrid, kTwThreads, TwCfg<B, S, true>::kSmemBytes, s->stream>>>(c);
             }
         });
-        return check_launch(s, upper ? "upper chunk sweep" : "lower chunk sweep");
+        return check_launch(s, upper ? "upper tile sweep" : "lower tile sweep");
     }
     const int grid = s->slice_grid();
     DISPATCH_B(s->b, {
@@ -451,7 +455,6 @@ int prec_update(opmb200_solver* s)
     a.trip_dst = s->trip_dst.p;
     a.row_static = s->row_static.p;
     a.dinv = s->dinv.p;
-    a.dinv_s = s->dinv_s.p;
     a.dinv_rec = s->dinv_rec.p;
     a.row_flag = s->row_flag.p;
     a.epoch = s->epoch;
@@ -467,12 +470,21 @@ int prec_update(opmb200_solver* s)
         else dilu_factor_kernel<B><<<grid, kCtaThreads, 0, s->stream>>>(a);
     });
     TRY(check_launch(s, "factorisation"));
-    if (s->schedule == 1 && s->L.n_slices > 0) { // chunk sweeps read step records, not the SELL slots
-        const int fgrid = std::max(1, std::min(s->num_sms * 8, (2 * s->L.n_slices + 7) / 8));
-        DISPATCH_B(s->b, (cw_stream_fill_kernel<B><<<fgrid, 256, 0, s->stream>>>(
-                          s->L.n_slices, s->slices.p, s->prec == PREC_ILU0 ? s->F.p : s->A.p, s->dinv_s.p, s->stream_lo.p,
-                          s->stream_up.p, s->prec == PREC_DILU ? 1 : 0)));
-        TRY(check_launch(s, "stream fill"));
+    if (s->L.schedule_mode == 1 && s->L.n_steps > 0) { // the tile walkers read step records, not the SELL slots
+        const double* M = s->prec == PREC_ILU0 ? s->F.p : s->A.p;
+        const int fgrid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)s->num_sms * 8, ((int64_t)s->L.n_steps * kTwWarps * 32 + 255) / 256));
+        for (int up = 0; up < 2; ++up) {
+            const bool with_dinv = up || s->prec == PREC_DILU;
+            DISPATCH_BS(s->b, s->L.tw_slots[up], {
+                if (with_dinv)
+                    tw_fill_kernel<B, S, true><<<fgrid, 256, 0, s->stream>>>(s->L.n_steps, up, s->step_q0.p, s->tw_slot[up].p, s->L.n, M,
+                                                                           s->dinv.p, s->tw_stream[up].p);
+                else
+                    tw_fill_kernel<B, S, false><<<fgrid, 256, 0, s->stream>>>(s->L.n_steps, up, s->step_q0.p, s->tw_slot[up].p, s->L.n, M,
+                                                                            s->dinv.p, s->tw_stream[up].p);
+            });
+            TRY(check_launch(s, "stream fill"));
+        }
     }
     return OPMB200_SUCCESS;
 }
@@ -550,12 +562,10 @@ int parse_options(opmb200_solver* s, const char* json)
         s->op_repeats = prm.get<int>("b200.operator_repeats", 1);
         s->throttle = prm.get<int>("b200.throttle_levels", 6);
         const std::string sched = prm.get<std::string>("b200.schedule", "levels");
-        if (sched != "levels" && sched != "chunks")
-            return fail(OPMB200_BAD_OPTIONS, "b200.schedule must be \"levels\" or \"chunks\"");
-        s->schedule = sched == "chunks" ? 1 : 0;
+        if (sched != "levels" && sched != "tiles" && sched != "chunks" && sched != "auto")
+            return fail(OPMB200_BAD_OPTIONS, "b200.schedule must be \"levels\", \"tiles\" or \"auto\"");
+        s->schedule = sched == "levels" ? 0 : (sched == "auto" ? 2 : 1);
         s->chunk_rows = prm.get<int>("b200.chunk_rows", 0);
-        s->prefetch = std::max(0, std::min(32, prm.get<int>("b200.prefetch_slices", 0)));
-        s->debug = prm.get<int>("b200.debug_timing", 0);
         s->use_graph = prm.get<int>("b200.cuda_graph", 1) != 0;
         s->trace = std::getenv("OPMB200_TRACE") != nullptr;
     } catch (const std::exception& e) {
@@ -828,8 +838,41 @@ int opmb200_plan_schedule(int block_size, int64_t n_rows, int64_t nnzb, const in
         std::copy(L.r2n.begin(), L.r2n.end(), position_to_row);
     if (slice_first)
         std::copy(L.slice_q0.begin(), L.slice_q0.begin() + L.n_slices + 1, slice_first);
-    if (chunk_first_slice && schedule == 1)
+    if (chunk_first_slice && L.schedule_mode == 1)
         std::copy(L.chunk_slice0.begin(), L.chunk_slice0.end(), chunk_first_slice);
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_plan_tiles(int block_size, int64_t n_rows, int64_t nnzb, const int32_t* rowptr, const int32_t* colidx,
+                       int64_t n_interior, int schedule, int chunk_rows, int32_t* info, int32_t* position_to_row,
+                       int32_t* step_first, int32_t* chunk_first_step, int32_t* step_flags, int direction,
+                       int32_t* codes, int32_t* ext, int32_t* n_ext)
+{
+    if (!info || direction < 0 || direction > 1)
+        return fail(OPMB200_INVALID_ARGUMENT, "bad arguments");
+    Layout L;
+    std::string err;
+    const int rc = build_layout(block_size, n_rows, nnzb, rowptr, colidx, n_interior, false, schedule, chunk_rows, L, err);
+    if (rc != OPMB200_SUCCESS)
+        return fail(rc, err);
+    const int32_t out[8] = {L.schedule_mode, L.tw_rows, L.tw_ring, L.tw_slots[0], L.tw_slots[1], L.n_steps, L.n_chunks, L.chunk_rows};
+    std::copy_n(out, 8, info);
+    if (position_to_row)
+        std::copy(L.r2n.begin(), L.r2n.end(), position_to_row);
+    if (L.schedule_mode != 1)
+        return OPMB200_SUCCESS;
+    if (step_first)
+        std::copy(L.step_q0.begin(), L.step_q0.end(), step_first);
+    if (chunk_first_step)
+        std::copy(L.chunk_step0.begin(), L.chunk_step0.end(), chunk_first_step);
+    if (step_flags)
+        std::copy(L.step_flags.begin(), L.step_flags.end(), step_flags);
+    if (codes)
+        std::copy(L.tw_code[direction].begin(), L.tw_code[direction].end(), codes);
+    if (ext)
+        std::copy(L.tw_ext[direction].begin(), L.tw_ext[direction].end(), ext);
+    if (n_ext)
+        std::copy(L.tw_next[direction].begin(), L.tw_next[direction].end(), n_ext);
     return OPMB200_SUCCESS;
 }
 
@@ -941,55 +984,58 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
                              L.slice_wu[i], L.slice_level[i], L.slice_lrank[i], 0};
     CUDA_TRY(s->slices.upload(meta, st));
     CUDA_TRY(s->slot_col.upload(L.slot_col, st));
-    std::vector<int32_t> rec_lo, rec_up; // header + column positions of every step record (host staging)
-    if (s->schedule == 1 && s->prec != PREC_NONE && L.n_slices > 0) {
-        size_t rec_bytes_lo = 0, rec_bytes_up = 0;
-        DISPATCH_B(block_size, {
-            rec_bytes_lo = (size_t)cw_record_bytes<B>(s->prec == PREC_DILU);
-            rec_bytes_up = (size_t)cw_record_bytes<B>(true);
-        });
-        CUDA_TRY(s->stream_lo.alloc(rec_bytes_lo * L.n_slices));
-        CUDA_TRY(s->stream_up.alloc(rec_bytes_up * L.n_slices));
-        constexpr int kStatic = 128; // ints: 32 header + kPrefetch*32 columns (CwSmem::kBlkOff bytes)
-        rec_lo.assign((size_t)L.n_slices * kStatic, -1);
-        rec_up.assign((size_t)L.n_slices * kStatic, -1);
-        for (int i = 0; i < L.n_slices; ++i) {
-            const int q0 = L.slice_q0[i], cnt = L.slice_q0[i + 1] - L.slice_q0[i];
-            const int wl = L.slice_wl[i], wu = L.slice_wu[i], base = L.slice_base[i];
-            int32_t* lo = rec_lo.data() + (size_t)i * kStatic;
-            int32_t* up = rec_up.data() + (size_t)(L.n_slices - 1 - i) * kStatic;
-            lo[0] = q0, lo[1] = cnt, lo[2] = wl, lo[3] = base;
-            up[0] = q0, up[1] = cnt, up[2] = wu, up[3] = base + wl + 1;
-            auto is_ext = [](int32_t c) { return c >= 0 && !(c & kRingFlag); };
-            bool ext_lo = wl > kPrefetch, ext_up = wu > kPrefetch; // wide rows resolve their own dependencies
-            for (int k = 0; k < kPrefetch; ++k)
-                for (int lane = 0; lane < kSlice; ++lane) {
-                    if (k < wl) {
-                        const int32_t c = L.sweep_col[((size_t)base + k) * kSlice + lane];
-                        lo[32 + k * 32 + lane] = c;
-                        ext_lo = ext_lo || is_ext(c);
-                    }
-                    if (k < wu) {
-                        const int32_t c = L.sweep_col[((size_t)base + wl + 1 + k) * kSlice + lane];
-                        up[32 + k * 32 + lane] = c;
-                        ext_up = ext_up || is_ext(c);
-                    }
-                }
-            if (ext_lo)
-                lo[2] |= kCwHasExt;
-            if (ext_up)
-                up[2] |= kCwHasExt;
+    if (L.schedule_mode == 1 && s->prec != PREC_NONE && L.n_steps > 0) {
+        // step records of the tile walkers: the static head of every record (header, external list,
+        // dependency codes) is written here once, the values after every factorisation (tw_fill_kernel)
+        const int RP = L.tw_rp();
+        for (int up = 0; up < 2; ++up) {
+            const int S = L.tw_slots[up];
+            const bool with_dinv = up || s->prec == PREC_DILU;
+            size_t rec_bytes = 0, head_bytes = 0;
+            int ring = 0;
+            DISPATCH_BS(block_size, S, {
+                rec_bytes = with_dinv ? TwCfg<B, S, true>::kRecBytes : TwCfg<B, S, false>::kRecBytes;
+                head_bytes = TwCfg<B, S, true>::kValOff;
+                ring = TwCfg<B, S, true>::RING;
+                static_assert(TwCfg<B, S, true>::kValOff == TwCfg<B, S, false>::kValOff, "record heads agree");
+            });
+            if (ring != L.tw_ring || (int)(head_bytes / 4) < 4 + kTwMaxExt + S * RP)
+                return fail(OPMB200_INVALID_ARGUMENT, "tile walker tables do not match the kernels' record layout");
+            const size_t hw = head_bytes / 4;
+            std::vector<int32_t> head((size_t)L.n_steps * hw, -1);
+            for (int st_ = 0; st_ < L.n_steps; ++st_) {
+                int32_t* h = head.data() + (size_t)(up ? L.n_steps - 1 - st_ : st_) * hw;
+                h[0] = L.step_q0[st_];
+                h[1] = L.step_q0[st_ + 1] - L.step_q0[st_];
+                h[2] = L.tw_next[up][st_];
+                h[3] = L.step_flags[st_];
+                std::copy_n(L.tw_ext[up].begin() + (size_t)st_ * kTwMaxExt, kTwMaxExt, h + 4);
+                std::copy_n(L.tw_code[up].begin() + (size_t)st_ * S * RP, (size_t)S * RP, h + 4 + kTwMaxExt);
+            }
+            CUDA_TRY(s->tw_stream[up].alloc(rec_bytes * L.n_steps));
+            CUDA_TRY(cudaMemcpy2D(s->tw_stream[up].p, rec_bytes, head.data(), head_bytes, head_bytes, L.n_steps,
+                                  cudaMemcpyHostToDevice));
+            CUDA_TRY(s->tw_slot[up].upload(L.tw_slot[up], st));
         }
-        CUDA_TRY(cudaMemcpy2DAsync(s->stream_lo.p, rec_bytes_lo, rec_lo.data(), kStatic * 4, kStatic * 4, L.n_slices,
-                                   cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpy2DAsync(s->stream_up.p, rec_bytes_up, rec_up.data(), kStatic * 4, kStatic * 4, L.n_slices,
-                                   cudaMemcpyHostToDevice, st));
+        CUDA_TRY(s->step_q0.upload(L.step_q0, st));
+        CUDA_TRY(s->chunk_step0.upload(L.chunk_step0, st));
+        DISPATCH_BS(block_size, L.tw_slots[0], {
+            CUDA_TRY(cudaFuncSetAttribute(tw_sweep_kernel<B, S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          TwCfg<B, S, false>::kSmemBytes));
+            CUDA_TRY(cudaFuncSetAttribute(tw_sweep_kernel<B, S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          TwCfg<B, S, true>::kSmemBytes));
+        });
+        DISPATCH_BS(block_size, L.tw_slots[1], {
+            CUDA_TRY(cudaFuncSetAttribute(tw_sweep_kernel<B, S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          TwCfg<B, S, true>::kSmemBytes));
+            CUDA_TRY(cudaFuncSetAttribute(tw_sweep_kernel<B, S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          TwCfg<B, S, true>::kSmemBytes));
+        });
     }
     CUDA_TRY(s->slot_src.upload(L.slot_src, st));
     CUDA_TRY(s->r2n.upload(L.r2n, st));
     CUDA_TRY(s->n2r.upload(L.n2r, st));
     CUDA_TRY(s->level_q0.upload(L.level_q0, st));
-    CUDA_TRY(s->chunk_slice0.upload(L.chunk_slice0, st));
     CUDA_TRY(s->l_transpose.upload(L.l_transpose, st));
     if (s->prec == PREC_ILU0) {
         CUDA_TRY(s->trip_ptr.upload(L.trip_ptr, st));
@@ -1001,8 +1047,6 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
     CUDA_TRY(s->A.alloc((size_t)L.n_slot_rows * kSlice * BB));
     CUDA_TRY(s->dinv.alloc((size_t)L.n * BB));
     CUDA_TRY(s->dinv_rec.alloc((size_t)L.n * block_size * (block_size <= 2 ? 2 : 4)));
-    CUDA_TRY(s->dinv_s.alloc((size_t)std::max(L.n_slices, 1) * kSlice * BB));
-    CUDA_TRY(cudaMemsetAsync(s->dinv_s.p, 0, s->dinv_s.n * sizeof(double), st));
     CUDA_TRY(s->row_flag.alloc((size_t)L.n));
     CUDA_TRY(cudaMemsetAsync(s->row_flag.p, 0, std::max<size_t>(L.n, 1) * sizeof(int), st));
     CUDA_TRY(s->vals_native.alloc((size_t)nnzb * BB));
@@ -1063,15 +1107,6 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
         const size_t arena_bytes = align(s->off_ack + (size_t)kMaxNeighbors * sizeof(int));
         CUDA_TRY(s->arena.alloc(arena_bytes));
         CUDA_TRY(cudaMemsetAsync(s->arena.p, 0, arena_bytes, st));
-    }
-    if (s->schedule == 1) {
-        DISPATCH_B(block_size, {
-            constexpr int smem = CwSmem<B>::kCtaBytes;
-            CUDA_TRY(cudaFuncSetAttribute(cw_sweep_kernel<B, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CUDA_TRY(cudaFuncSetAttribute(cw_sweep_kernel<B, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CUDA_TRY(cudaFuncSetAttribute(cw_sweep_kernel<B, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-            CUDA_TRY(cudaFuncSetAttribute(cw_sweep_kernel<B, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        });
     }
     CUDA_TRY(cudaStreamSynchronize(st));
     *out = s.release();
@@ -1213,7 +1248,7 @@ int opmb200_get_info(opmb200_solver* s, opmb200_info* info)
     info->t_update_ms = s->t_update_ms;
     info->t_solve_ms = s->t_solve_ms;
     info->kernel_launches = s->launches;
-    info->schedule = s->schedule;
+    info->schedule = s->L.schedule_mode;
     info->n_chunks = s->L.n_chunks;
     info->chunk_rows = s->L.chunk_rows;
     info->est_steps = s->L.est_steps;
@@ -1384,28 +1419,6 @@ int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, doubl
     return OPMB200_SUCCESS;
 }
 
-
-#ifdef OPMB200_PROFILE
-extern "C" int opmb200_prof_read(unsigned long long* out16, int reset)
-{
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out16, g_prof, sizeof(unsigned long long) * 16);
-    if (reset) {
-        unsigned long long z[16] = {0};
-        cudaMemcpyToSymbol(g_prof, z, sizeof z);
-    }
-    return 0;
-}
-#endif
-
-#ifdef OPMB200_PROFILE
-extern "C" int opmb200_prof_chunks(unsigned long long* out, int nchunks)
-{
-    cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out, g_chunk_t, sizeof(unsigned long long) * 3 * (size_t)std::min(nchunks, 4096));
-    return 0;
-}
-#endif
 
 namespace {
 struct P2PBlob {

@@ -15,18 +15,19 @@ import os
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-10
-# the whole file runs once per sweep schedule: OPMB200_TEST_SCHEDULE=levels|chunks (default: both via the fixture)
+# the whole file runs once per sweep schedule (the fixture below)
 
 
-_SCHEDULE = {"name": os.environ.get("OPMB200_TEST_SCHEDULE", "chunks"), "chunk_rows": 0}
+_SCHEDULE = {"name": "tiles", "chunk_rows": 0}
 
 
-@pytest.fixture(autouse=True, params=["levels", "chunks", "chunks64"])
+@pytest.fixture(autouse=True, params=["levels", "tiles", "tiles64"])
 def schedule(request):
-    """every test runs with the level-scheduled sweeps, the chunked wavefronts (automatic chunk size) and
-    deliberately tiny chunks (64 rows: many chunk-boundary dependencies, ring wrap-around)"""
-    _SCHEDULE["name"] = "levels" if request.param == "levels" else "chunks"
-    _SCHEDULE["chunk_rows"] = 64 if request.param == "chunks64" else 0
+    """every test runs with the level-scheduled sweeps, the tile walkers (automatic chunk / tile choice; patterns
+    with rows wider than 4 slots keep the level schedule) and deliberately tiny contiguous chunks (64 rows: many
+    chunk-boundary dependencies, ring wrap-around)"""
+    _SCHEDULE["name"] = "levels" if request.param == "levels" else "tiles"
+    _SCHEDULE["chunk_rows"] = 64 if request.param == "tiles64" else 0
     yield request.param
 
 
@@ -200,7 +201,12 @@ def test_bicgstab_solve_parity(cfg, scale, prec, tol, pk):
         k = min(len(h), len(ho), 12)
         assert np.allclose(h[:k], ho[:k], rtol=1e-6), (h[:k], ho[:k])
         if len(h) == len(ho):  # same stopping half-step: solutions agree to rounding
-            assert rel_err(x, xo) < 1e-8, rel_err(x, xo)
+            # measured (profiles/r02_solution_error.md): 1e-15..4e-14 at Flow's tol 1e-2 on every BASELINE config,
+            # with or without FMA contraction; beyond ~40 iterations BiCGSTAB's trajectories separate (the dot
+            # products are tree sums here, running sums there) and two solutions that both meet `tol` agree to
+            # ~tol/100 only -- a property of the Krylov recurrence, not of a kernel (the preconditioner apply
+            # itself is bit-identical to the oracle without FMA and within 1e-15 with it)
+            assert rel_err(x, xo) < (1e-10 if tol >= 1e-4 else 1e-8), rel_err(x, xo)
             assert np.allclose(h, ho, rtol=1e-2)
             # the residual vector Dune leaves in b
             res_true = s[rhs_name] - orc.spmv(A.rowptr, A.col, A.val, x)
@@ -297,6 +303,33 @@ def test_singular_4x4_block_is_matrix_block_error():
     assert fs.apply(x, r).converged
 
 
+@pytest.mark.parametrize("prec", ["dilu", "ilu0"])
+def test_tiny_determinant_4x4_blocks_take_the_lu_fallback(prec):
+    """matrixblock.hh:192-224: a 4x4 pivot block with |det| < 1e-40 is inverted by pivoted LU, not by the
+    adjugate formula.  A whole system scaled by 1e-14 has |det(A_ii)| < 1e-45 in every row (and so have the
+    eliminated pivots), so every block inverse of the factorisation takes that path on the GPU; the factors
+    must match the oracle's (which takes the same path, test_invert_block4_lu_fallback_and_singular) and the
+    inverse of the scaled block is 1e14 times the inverse of the unscaled one."""
+    A = SYSTEMS["blackoil_b4"].copy()
+    A.val *= 1e-14
+    assert np.abs(np.linalg.det(A.val[A.diag_index()])).max() < 1e-40
+    fs = FlexibleSolver(MatrixAdapter(A), opts(prec, tol=1e-8))
+    ps = orc.ParSystem.serial(A.rowptr, A.col, A.val)
+    ps.prec_update(prec)
+    if prec == "dilu":
+        assert rel_err(fs.dinv(), ps.dinv()) < TOL
+    else:
+        assert rel_err(fs.ilu0(), ps.lu()) < TOL
+    d = np.random.default_rng(4).standard_normal(A.n * 4)
+    v = np.zeros(A.n * 4)
+    fs.preconditioner().apply(v, d)
+    assert rel_err(v, ps.prec_apply([d])[0]) < TOL
+    x, r = np.zeros(A.n * 4), d.copy()
+    res = fs.apply(x, r)
+    xo, ro, _ = orc.solve_serial(A.rowptr, A.col, A.val, d, prec=prec, tol=1e-8)
+    assert res.converged and abs(res.iterations - ro["iterations"]) <= 1 and rel_err(x, xo) < 1e-6
+
+
 def test_device_pointers_are_accepted():
     torch = pytest.importorskip("torch")
     s = generators.config("C2", scale=0.3)
@@ -339,21 +372,23 @@ def test_wide_rows_beyond_the_register_window():
 
 @pytest.mark.parametrize("b,prec", [(3, "dilu"), (3, "ilu0"), (4, "dilu"), (2, "ilu0")])
 def test_tile_chunks_equal_the_level_schedule_bit_for_bit(b, prec, schedule):
-    """box grid cut into 8x4 tiles of grid lines (the shape the planner picks for C3): on a 7-point pattern
-    every row has at most 3 lower / 3 upper blocks, all schedules add them in the reference's order, so the
-    preconditioner apply of the chunk sweeps must equal the level sweeps' bit for bit -- and the oracle to 1e-10"""
-    if schedule != "chunks":
+    """box grid cut into tiles of grid lines, one line per row of a CTA step (4 warps x 32/b rows: 10x4 and 20x2
+    for b = 3): on a 7-point pattern every row has at most 3 lower / 3 upper blocks, all schedules add them in the
+    reference's order, so the preconditioner apply of the tile walkers must equal the level sweeps' bit for bit --
+    and the oracle to 1e-10"""
+    if schedule != "tiles":
         pytest.skip("compares the two schedules itself")
     s = generators.blackoil_system(24, 40, 12, b=b, seed=21)
     A = s["A"]
     d = s["rhs2"]
     out = {}
-    for name, b200 in (("levels", {"schedule": "levels"}), ("tiles", {"schedule": "chunks", "chunk_rows": -804}),
-                       ("strips", {"schedule": "chunks", "chunk_rows": -1602})):
+    rows = 4 * (32 // b)
+    for name, b200 in (("levels", {"schedule": "levels"}), ("tiles", {"schedule": "tiles", "chunk_rows": -(rows // 4 * 100 + 4)}),
+                       ("strips", {"schedule": "tiles", "chunk_rows": -(rows // 2 * 100 + 2)})):
         fs = FlexibleSolver(MatrixAdapter(A), {"solver": "bicgstab", "tol": 1e-6, "maxiter": 100,
                                               "preconditioner": {"type": prec}, "b200": b200})
         if name != "levels":
-            assert fs.info()["chunk_rows"] == b200["chunk_rows"] and fs.info()["n_chunks"] > 4
+            assert fs.info()["schedule"] == 1 and fs.info()["chunk_rows"] == b200["chunk_rows"] and fs.info()["n_chunks"] > 4
         v = np.zeros_like(d)
         fs.preconditioner().apply(v, d)
         x, r = np.zeros_like(d), d.copy()

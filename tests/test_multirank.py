@@ -50,6 +50,6 @@ def test_two_rank_block_jacobi_chunk_schedule(prec):
     ghost rows ParallelOverlappingILU0 leaves alone)"""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    r = launch(2, ["--mode", "gpu", "--prec", prec, "--b", "3", "--collectives", "p2p", "--schedule", "chunks"],
+    r = launch(2, ["--mode", "gpu", "--prec", prec, "--b", "3", "--collectives", "p2p", "--schedule", "tiles"],
                29660 + (1 if prec == "ilu0" else 0))
     assert r.returncode == 0 and "MGPU_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
