@@ -31,8 +31,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
            "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    if os.environ.get("OPMB200_PROFILE"):  # in-kernel phase profile of the chunk sweeps (scripts/prof_chunk.py)
+    if os.environ.get("OPMB200_PROFILE"):  # in-kernel phase profile of the tile walkers (scripts/prof_tiles.py)
         cmd += ["-DOPMB200_PROFILE"]
+    if os.environ.get("OPMB200_TWDBG"):  # b200.debug_timing switches parts of the tile walkers off (timing only)
+        cmd += ["-DOPMB200_TWDBG"]
     cmd += os.environ.get("OPMB200_EXTRA_FLAGS", "").split()  # design experiments (-DCW_...=)
     cmd += [os.path.join(CSRC, s) for s in SOURCES]
     cmd += ["-lnccl"]

@@ -597,15 +597,17 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
         L.tw_ext[d].clear();
         L.tw_next[d].clear();
         L.tw_slot[d].clear();
+        L.tw_pub[d].clear();
     }
     if (schedule_mode == 1) {
         const int RP = L.tw_rp();
         for (int d = 0; d < 2; ++d) {
             const int S = L.tw_slots[d];
-            L.tw_code[d].assign((size_t)L.n_steps * S * RP, -1);
+            L.tw_code[d].assign((size_t)L.n_steps * S * RP, kTwRing | L.tw_ring); // "no dependency": the zero record behind the ring
             L.tw_ext[d].assign((size_t)L.n_steps * kTwMaxExt, -1);
             L.tw_next[d].assign(L.n_steps, 0);
             L.tw_slot[d].assign((size_t)S * n, -1);
+            L.tw_pub[d].assign((size_t)L.n_steps * 4, 0);
         }
         for (int32_t st = 0; st < L.n_steps; ++st) {
             for (int32_t q = L.step_q0[st]; q < L.step_q0[st + 1]; ++q) {
@@ -633,6 +635,18 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
                 }
             }
         }
+        // rows somebody polls
+        std::vector<int32_t> step_of(n);
+        for (int32_t st = 0; st < L.n_steps; ++st)
+            for (int32_t q = L.step_q0[st]; q < L.step_q0[st + 1]; ++q)
+                step_of[q] = st;
+        for (int d = 0; d < 2; ++d)
+            for (int32_t st = 0; st < L.n_steps; ++st)
+                for (int l = 0; l < L.tw_next[d][st]; ++l) {
+                    const int32_t pp = L.tw_ext[d][(size_t)st * kTwMaxExt + l];
+                    const int rho = pp - L.step_q0[step_of[pp]];
+                    L.tw_pub[d][(size_t)step_of[pp] * 4 + (rho >> 5)] |= (int32_t)(1u << (rho & 31));
+                }
     }
 
     // ---- DILU transposed-entry map and ILU0 update pairs -------------------------------------------

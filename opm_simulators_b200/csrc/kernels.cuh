@@ -158,6 +158,15 @@ __device__ __forceinline__ void rec_store_strong(double* base, size_t q, const d
                      : "memory");
     }
 }
+// plain store of a record nobody polls while this kernel runs (a later kernel reads it)
+template <int B>
+__device__ __forceinline__ void rec_store_weak(double* base, size_t q, const double (&x)[B])
+{
+    double2* p = reinterpret_cast<double2*>(base + q * Rec<B>::W);
+    p[0] = make_double2(x[0], B >= 2 ? x[B >= 2 ? 1 : 0] : 0.0);
+    if constexpr (Rec<B>::W == 4)
+        p[1] = make_double2(x[B >= 3 ? 2 : 0], B == 4 ? x[B - 1] : 0.0);
+}
 template <int B>
 __device__ __forceinline__ void rec_store_sentinel(double* base, size_t q)
 {
@@ -1396,6 +1405,16 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
 {
     unsigned ok;
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(smem_u32(bar)), "r"(parity)
+                 : "memory");
+    return ok != 0;
+}
+// non-blocking test of a phase (try_wait may suspend the thread until a time limit)
+__device__ __forceinline__ bool mbar_test_wait(unsigned long long* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok)
                  : "r"(smem_u32(bar)), "r"(parity)
                  : "memory");

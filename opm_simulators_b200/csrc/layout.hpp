@@ -78,10 +78,13 @@ struct Layout {
     std::vector<int32_t> step_flags;  // [n_steps] bit 0: the step's rows are ghost rows
     // per direction d (0 lower, 1 upper), by step s (NOT in walking order):
     //   tw_code[d][(s*S + k)*RP + rho]: where row rho of the step finds dependency k:
-    //        -1 none | kTwRing + ring index | kTwExt + slot of the step's external list
+    //        kTwRing + tw_ring none (the zero record behind the ring) | kTwRing + ring index | kTwExt + slot of the
+    //        step's external list
     //   tw_ext[d][s*32 + l]: position of external dependency l (-1 beyond tw_next[d][s])
     //   tw_slot[d][k*n + q]: SELL slot of dependency block k of the row at position q (-1 none)
-    std::vector<int32_t> tw_code[2], tw_ext[2], tw_next[2], tw_slot[2];
+    //   tw_pub[d][s*4 + w]: bit rho of word w set = some other chunk (or a far step of this one) polls the
+    //        result of row rho of the step: it is published with a strong store
+    std::vector<int32_t> tw_code[2], tw_ext[2], tw_next[2], tw_slot[2], tw_pub[2];
     int tw_rp() const { return (tw_rows + 3) & ~3; }
     // DILU: for every L slot (compact L numbering) the slot of the transposed block, or -1
     std::vector<int32_t> l_transpose; // [n_l_slot_rows*32]

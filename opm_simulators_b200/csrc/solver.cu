@@ -121,6 +121,9 @@ struct opmb200_solver {
     int throttle = 6;
     int schedule = 0;   // requested: 0 levels, 1 tiles, 2 auto (what was built: L.schedule_mode)
     int chunk_rows = 0; // > 0 contiguous chunks, 0 automatic, < 0 a tile shape
+    int prefetch = 12;  // tile walkers: L2 look-ahead of the loader warp, in steps (<= 32)
+    int poll_warps = 3; // tile walkers: warps polling the dependencies that cross a chunk boundary (1..3)
+    int debug = 0;      // OPMB200_TWDBG builds: timing experiments (wrong results)
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -388,6 +391,11 @@ int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
         c.v = a.v;
         c.n = a.n;
         c.ghost_zero = a.ghost_zero;
+        c.step_q0 = s->step_q0.p;
+        c.prefetch = s->prefetch;
+        c.debug = s->debug;
+        c.poll_warps = s->poll_warps;
+        const int threads = (kTwWarps + 1 + s->poll_warps) * 32;
         c.ticket = a.ticket;
         c.sc = a.sc;
         c.check_done = a.check_done;
@@ -395,11 +403,11 @@ int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
         const bool ilu0 = s->prec == PREC_ILU0;
         DISPATCH_BS(s->b, s->L.tw_slots[upper ? 1 : 0], {
             if (ilu0) {
-                if (upper) tw_sweep_kernel<B, S, true, true><<<cgrid, kTwThreads, TwCfg<B, S, true>::kSmemBytes, s->stream>>>(c);
-                else tw_sweep_kernel<B, S, true, false><<<cgrid, kTwThreads, TwCfg<B, S, false>::kSmemBytes, s->stream>>>(c);
+                if (upper) tw_sweep_kernel<B, S, true, true><<<cgrid, threads, TwCfg<B, S, true, true>::kSmemBytes, s->stream>>>(c);
+                else tw_sweep_kernel<B, S, true, false><<<cgrid, threads, TwCfg<B, S, false, false>::kSmemBytes, s->stream>>>(c);
             } else {
-                if (upper) tw_sweep_kernel<B, S, false, true><<<cgrid, kTwThreads, TwCfg<B, S, true>::kSmemBytes, s->stream>>>(c);
-                else tw_sweep_kernel<B, S, false, false><<<cgrid, kTwThreads, TwCfg<B, S, true>::kSmemBytes, s->stream>>>(c);
+                if (upper) tw_sweep_kernel<B, S, false, true><<<cgrid, threads, TwCfg<B, S, true, true>::kSmemBytes, s->stream>>>(c);
+                else tw_sweep_kernel<B, S, false, false><<<cgrid, threads, TwCfg<B, S, true, false>::kSmemBytes, s->stream>>>(c);
             }
         });
         return check_launch(s, upper ? "upper tile sweep" : "lower tile sweep");
@@ -566,6 +574,9 @@ int parse_options(opmb200_solver* s, const char* json)
             return fail(OPMB200_BAD_OPTIONS, "b200.schedule must be \"levels\", \"tiles\" or \"auto\"");
         s->schedule = sched == "levels" ? 0 : (sched == "auto" ? 2 : 1);
         s->chunk_rows = prm.get<int>("b200.chunk_rows", 0);
+        s->prefetch = std::max(0, std::min(32, prm.get<int>("b200.prefetch_steps", 12)));
+        s->poll_warps = std::max(1, std::min(kTwMaxPollWarps, prm.get<int>("b200.poll_warps", 3)));
+        s->debug = prm.get<int>("b200.debug_timing", 0);
         s->use_graph = prm.get<int>("b200.cuda_graph", 1) != 0;
         s->trace = std::getenv("OPMB200_TRACE") != nullptr;
     } catch (const std::exception& e) {
@@ -994,23 +1005,26 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
             size_t rec_bytes = 0, head_bytes = 0;
             int ring = 0;
             DISPATCH_BS(block_size, S, {
-                rec_bytes = with_dinv ? TwCfg<B, S, true>::kRecBytes : TwCfg<B, S, false>::kRecBytes;
-                head_bytes = TwCfg<B, S, true>::kValOff;
-                ring = TwCfg<B, S, true>::RING;
-                static_assert(TwCfg<B, S, true>::kValOff == TwCfg<B, S, false>::kValOff, "record heads agree");
+                rec_bytes = with_dinv ? TwCfg<B, S, true, true>::kRecBytes : TwCfg<B, S, false, false>::kRecBytes;
+                head_bytes = TwCfg<B, S, true, true>::kValOff;
+                ring = TwCfg<B, S, true, true>::RING;
+                static_assert(TwCfg<B, S, true, true>::kValOff == TwCfg<B, S, false, false>::kValOff, "record heads agree");
+                static_assert(TwCfg<B, S, true, true>::kRecBytes == TwCfg<B, S, true, false>::kRecBytes, "records do not depend on the direction");
             });
-            if (ring != L.tw_ring || (int)(head_bytes / 4) < 4 + kTwMaxExt + S * RP)
+            if (ring != L.tw_ring || (int)(head_bytes / 4) < 12 + kTwMaxExt + S * RP)
                 return fail(OPMB200_INVALID_ARGUMENT, "tile walker tables do not match the kernels' record layout");
             const size_t hw = head_bytes / 4;
-            std::vector<int32_t> head((size_t)L.n_steps * hw, -1);
+            std::vector<int32_t> head((size_t)L.n_steps * hw, kTwRing | L.tw_ring); // rows beyond a step's count: no dependency
             for (int st_ = 0; st_ < L.n_steps; ++st_) {
                 int32_t* h = head.data() + (size_t)(up ? L.n_steps - 1 - st_ : st_) * hw;
                 h[0] = L.step_q0[st_];
                 h[1] = L.step_q0[st_ + 1] - L.step_q0[st_];
                 h[2] = L.tw_next[up][st_];
                 h[3] = L.step_flags[st_];
-                std::copy_n(L.tw_ext[up].begin() + (size_t)st_ * kTwMaxExt, kTwMaxExt, h + 4);
-                std::copy_n(L.tw_code[up].begin() + (size_t)st_ * S * RP, (size_t)S * RP, h + 4 + kTwMaxExt);
+                std::copy_n(L.tw_pub[up].begin() + (size_t)st_ * 4, 4, h + 4);      // polled in this sweep
+                std::copy_n(L.tw_pub[1 - up].begin() + (size_t)st_ * 4, 4, h + 8);  // polled in the other sweep
+                std::copy_n(L.tw_ext[up].begin() + (size_t)st_ * kTwMaxExt, kTwMaxExt, h + 12);
+                std::copy_n(L.tw_code[up].begin() + (size_t)st_ * S * RP, (size_t)S * RP, h + 12 + kTwMaxExt);
             }
             CUDA_TRY(s->tw_stream[up].alloc(rec_bytes * L.n_steps));
             CUDA_TRY(cudaMemcpy2D(s->tw_stream[up].p, rec_bytes, head.data(), head_bytes, head_bytes, L.n_steps,
@@ -1021,15 +1035,15 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
         CUDA_TRY(s->chunk_step0.upload(L.chunk_step0, st));
         DISPATCH_BS(block_size, L.tw_slots[0], {
             CUDA_TRY(cudaFuncSetAttribute(tw_sweep_kernel<B, S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          TwCfg<B, S, false>::kSmemBytes));
+                                          TwCfg<B, S, false, false>::kSmemBytes));
             CUDA_TRY(cudaFuncSetAttribute(tw_sweep_kernel<B, S, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          TwCfg<B, S, true>::kSmemBytes));
+                                          TwCfg<B, S, true, false>::kSmemBytes));
         });
         DISPATCH_BS(block_size, L.tw_slots[1], {
             CUDA_TRY(cudaFuncSetAttribute(tw_sweep_kernel<B, S, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          TwCfg<B, S, true>::kSmemBytes));
+                                          TwCfg<B, S, true, true>::kSmemBytes));
             CUDA_TRY(cudaFuncSetAttribute(tw_sweep_kernel<B, S, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          TwCfg<B, S, true>::kSmemBytes));
+                                          TwCfg<B, S, true, true>::kSmemBytes));
         });
     }
     CUDA_TRY(s->slot_src.upload(L.slot_src, st));
@@ -1052,8 +1066,8 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
     CUDA_TRY(s->vals_native.alloc((size_t)nnzb * BB));
     const size_t len = (size_t)L.n * block_size;
     for (DevBuf<double>* v : {&s->vx, &s->vr, &s->vp, &s->vv, &s->vt, &s->vy, &s->vrt, &s->vw, &s->nat0, &s->nat1}) {
-        CUDA_TRY(v->alloc(len));
-        CUDA_TRY(cudaMemsetAsync(v->p, 0, std::max<size_t>(len, 1) * sizeof(double), st));
+        CUDA_TRY(v->alloc(len + 2)); // two doubles of slack: the tile walkers copy 16-byte aligned supersets of a run
+        CUDA_TRY(cudaMemsetAsync(v->p, 0, (len + 2) * sizeof(double), st));
     }
     s->vec_grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)s->num_sms * 8, ((int64_t)len + 255) / 256));
     s->max_grid = (std::max(s->vec_grid, s->slice_grid()) + 3) & ~3; // multiple of 4: grid_reduce reads 4 partials per load
@@ -1419,6 +1433,19 @@ int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, doubl
     return OPMB200_SUCCESS;
 }
 
+
+#ifdef OPMB200_PROFILE
+extern "C" int opmb200_prof_read(unsigned long long* out32, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out32, g_twp, sizeof(unsigned long long) * 40);
+    if (reset) {
+        unsigned long long z[40] = {0};
+        cudaMemcpyToSymbol(g_twp, z, sizeof z);
+    }
+    return 0;
+}
+#endif
 
 namespace {
 struct P2PBlob {

@@ -2,32 +2,37 @@
 //
 // The level schedule pays one L2 round trip per level (C3: 363 levels x ~1 us).  Here ONE CTA walks
 // ONE CHUNK of rows -- on a box grid a tile of TJ x TK grid lines, one line per row of a step, the
-// lines skewed so that step s holds cell i = s - lj - lk of line (lj, lk) -- step after step:
-//   * B lanes per block row (one lane per row of the b x b blocks): a step of R = 4 warps x 32/b rows
-//     is ~60 instructions per warp, its dependent chain 9 DFMA + 1 shuffle round + 3 DFMA;
-//   * results travel from step to step through a shared-memory ring (one named barrier per step);
-//     only dependencies that cross a chunk boundary travel through the L2, and those are polled by
-//     separate POLL warps (sentinel-validated dependency records, as in sweep_kernel) which park the
-//     values in the stage -- the compute warps never touch global memory for input;
-//   * everything else a step needs is ONE contiguous record of a per-sweep stream (header, external
-//     list, dependency codes, the rows' block values lane by lane, Dinv): a LOADER warp brings it in
-//     with one TMA bulk copy (cp.async.bulk -> UBLKCP) per step into a ring of stages, plus the
-//     right-hand side (cp.async from the solver vector, or a second bulk copy of the lower sweep's
-//     records), all signalled on the stage's "full" mbarrier;
-//   * CTAs are persistent and take chunks through the in-order ticket, so a chunk only ever waits
-//     for chunks that are running or done.
-// The arithmetic per row is the level kernels' (same blocks, same order of the fused multiply-adds),
-// so both schedules give bit-identical preconditioner applications.
+// lines skewed so that step s holds cell i = s - lj - lk of line (lj, lk) -- step after step.
+// Warp roles of a CTA (all data of a step meet in one STAGE of shared memory):
+//   * 4 COMPUTE warps, B lanes per block row (one lane per row of the b x b blocks), R = 4 x 32/b rows
+//     per step.  Their input comes from shared memory only.  The dependent chain of a step is: the
+//     neighbours' results from the chunk's shared-memory ring (or the stage's external slots) -> 9 DFMA
+//     -> one shuffle round -> 3 DFMA -> ring -> one named barrier; the block values and the dependency
+//     codes of step t+1 are loaded while step t computes; the results are stored to global memory from
+//     the registers BEHIND the barrier (a barrier waits for the acknowledgement of strong stores in
+//     front of it: +200 cycles per step, measured), strongly only where another chunk polls them.
+//   * a LOADER warp (one lane): per step ONE TMA bulk copy (cp.async.bulk -> UBLKCP) of the step's
+//     record -- header, publish mask, external list, dependency codes, the rows' block values lane by
+//     lane, Dinv; one contiguous piece of a per-sweep stream -- completion on the stage's "data"
+//     mbarrier; the stream is pulled into the L2 a few steps ahead (UBLKPF).
+//   * POLL warps, each serving every n-th step: the step's right-hand side (from the solver vector or
+//     the lower sweep's records, in the L2 since the chunk started) and the dependencies that cross a
+//     chunk boundary, one lane per dependency: strong loads of sentinel-armed dependency records (as in
+//     sweep_kernel) until they are valid; both parked in the stage, signalled on its "ext" mbarrier.
+// CTAs are persistent and take chunks through the in-order ticket, so a chunk only ever waits for
+// chunks that are running or done.  The arithmetic per row is the level kernels' (same blocks, same
+// order of the fused multiply-adds): both schedules give bit-identical preconditioner applications.
 #pragma once
 #include "kernels.cuh"
 #include "layout.hpp"
 
 namespace opmb200 {
 
-constexpr int kTwPollWarps = 3;
-constexpr int kTwThreads = (kTwWarps + 1 + kTwPollWarps) * 32;
+constexpr int kTwMaxPollWarps = 3;
+// launch bound (8 warps: 128 registers per thread with two CTAs per SM); the launch picks the poll warps
+constexpr int kTwMaxThreads = (kTwWarps + 1 + kTwMaxPollWarps) * 32;
 
-template <int B, int S, bool DINV>
+template <int B, int S, bool DINV, bool UPPER>
 struct TwCfg {
     static constexpr int NW = kTwWarps;               // compute warps
     static constexpr int RPW = 32 / B;                // rows per warp
@@ -39,34 +44,45 @@ struct TwCfg {
     static constexpr int RING = (4 * R <= 256) ? 256 : 512; // == Layout::tw_ring
     // record (global memory) == head of a stage (shared memory)
     static constexpr int kHdrOff = 0;                                // int4 {q0, count, n_ext, flags}
-    static constexpr int kExtPosOff = 16;                            // kTwMaxExt positions
+    static constexpr int kPubOff = 16;                               // 128 bits: rows whose result somebody polls in this sweep
+    static constexpr int kArmOff = 32;                               // 128 bits: rows somebody polls in the other sweep
+    static constexpr int kExtPosOff = 48;                            // kTwMaxExt positions
     static constexpr int kCodeOff = kExtPosOff + kTwMaxExt * 4;      // [S][RP] dependency codes
     static constexpr int kValOff = (kCodeOff + S * RP * 4 + 15) & ~15; // [NW][NP][32] double2
     static constexpr int kRecBytes = kValOff + NW * NP * 512;
-    // what the loaders add to a stage
-    static constexpr int kRhsOff = kRecBytes;                        // [RP][W] doubles
-    static constexpr int kExtValOff = kRhsOff + RP * W * 8;          // [kTwMaxExt][4] doubles
+    // what the loader and the poll warps add to a stage.  Right-hand side: upper = the lower sweep's records
+    // [RP][W]; lower = the step's runs of the component-major solver vector [B][RP]
+    static constexpr int kRhsOff = kRecBytes;
+    static constexpr int kRhsBytes = UPPER ? RP * W * 8 : B * RP * 8;
+    static constexpr int kExtValOff = kRhsOff + kRhsBytes;           // [kTwMaxExt][4] doubles
     static constexpr int kStageBytes = (kExtValOff + kTwMaxExt * 32 + 127) & ~127;
+    // stages: what fits in ~96 KB (two CTAs per SM)
     static constexpr int kStagesRaw = 98304 / kStageBytes;
-    static constexpr int kStages = kStagesRaw < 3 ? 3 : (kStagesRaw > 8 ? 8 : kStagesRaw);
+    static constexpr int kStages = kStagesRaw < 2 ? 2 : (kStagesRaw > 8 ? 8 : kStagesRaw);
     static constexpr int kRingOff = kStages * kStageBytes;           // [RING][4] doubles
     static constexpr int kZeroOff = kRingOff + RING * 32;            // one all-zero record
-    static constexpr int kBarOff = kZeroOff + 32;                    // kStages "full" mbarriers
-    static constexpr int kCtlOff = kBarOff + 8 * kStages;            // int[4]: progress, first record, steps, stop
-    static constexpr int kSmemBytes = kCtlOff + 16;
+    static constexpr int kBarOff = kZeroOff + 32;                    // kStages "data", then kStages "ext" mbarriers
+    static constexpr int kCtlOff = kBarOff + 16 * kStages;           // int[8], see TwCtl
+    static constexpr int kSmemBytes = kCtlOff + 32;
 };
+// control words in shared memory
+enum TwCtl { kCtlReleased = 0, kCtlRec0 = 1, kCtlSteps = 2, kCtlStop = 3, kCtlQ0 = 4, kCtlQ1 = 5 };
 
 struct TwArgs {
     int nchunks;
     const int* chunk_step0;      // [nchunks+1]
     int nsteps;
     const unsigned char* stream; // this sweep's step records in WALKING order (upper: reversed)
-    const double* d;             // lower: right-hand side (component-major)
+    const double* d;             // lower: right-hand side (component-major, two doubles of slack behind it)
     double* tmp;                 // dependency records of the lower sweep's result y
     double* vpoll;               // dependency records of the upper sweep's result
     double* v;                   // result, component-major like every solver vector
     int64_t n;
     int ghost_zero;              // ILU0 ghost rows: 1 = v enters as 0, 0 = keep v's input
+    const int* step_q0;          // [nsteps+1] first position of every step (NOT in walking order)
+    int prefetch;                // L2 look-ahead of the loader, in steps
+    int debug;                   // OPMB200_TWDBG builds only: timing experiments that switch parts off (wrong results)
+    int poll_warps;
     Ticket ticket;
     Scalars* sc;
     int check_done;
@@ -96,10 +112,6 @@ __device__ __forceinline__ void sts_f64(unsigned addr, double a)
 {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(a) : "memory");
 }
-__device__ __forceinline__ void sts_v2(unsigned addr, double a, double b)
-{
-    asm volatile("st.shared.v2.f64 [%0], {%1,%2};" ::"r"(addr), "d"(a), "d"(b) : "memory");
-}
 __device__ __forceinline__ void cp_async8(unsigned dst, const void* src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
@@ -109,57 +121,159 @@ __device__ __forceinline__ void cp_async_arrive_noinc(unsigned long long* bar)
 {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes)
+{
+    // cp.async.bulk.prefetch.L2 (SASS: UBLKPF.L2); address and size rounded to 16 bytes
+    const unsigned long long a = (unsigned long long)p;
+    const unsigned long long a0 = a & ~15ull;
+    const unsigned sz = (unsigned)(((a + bytes + 15ull) & ~15ull) - a0);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"(sz) : "memory");
+}
+
+#ifdef OPMB200_TWDBG
+#define TW_DBG(bit) (a.debug & (bit))
+#else
+#define TW_DBG(bit) false
+#endif
+
+#ifdef OPMB200_PROFILE
+// in-kernel profile of the tile walkers: cycles per phase, accumulated in registers by lane 0 of one warp per
+// role and flushed per chunk.  g_twp[0..7] compute phases, [8..15] loader phases, [16..23] poll phases,
+// [24] steps, [25] chunks, [26] poll loads issued, [28..35] store warp phases
+__device__ unsigned long long g_twp[40];
+#define TWP_DECL long long twp_t0__ = clock64(); unsigned long long twp_acc__[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TWP_MARK(i)                                                                                                    \
+    do {                                                                                                               \
+        const long long now__ = clock64();                                                                             \
+        twp_acc__[i] += (unsigned long long)(now__ - twp_t0__);                                                        \
+        twp_t0__ = now__;                                                                                              \
+    } while (0)
+#define TWP_FLUSH(base, cond)                                                                                          \
+    do {                                                                                                               \
+        if (cond)                                                                                                      \
+            for (int i__ = 0; i__ < 8; ++i__)                                                                          \
+                atomicAdd(&g_twp[(base) + i__], twp_acc__[i__]);                                                       \
+    } while (0)
+#define TWP_COUNT(i, cond, v)                                                                                          \
+    do {                                                                                                               \
+        if (cond)                                                                                                      \
+            atomicAdd(&g_twp[i], (unsigned long long)(v));                                                             \
+    } while (0)
+#else
+#define TWP_DECL
+#define TWP_MARK(i)
+#define TWP_FLUSH(base, cond)
+#define TWP_COUNT(i, cond, v)
+#endif
+
+// what a compute lane holds about a step before its dependencies are there
+template <int B, int S, int NP>
+struct TwStep {
+    int q0, count, flags;
+    unsigned xaddr[S]; // where dependency s is found (ring, the stage's external slots, the zero record)
+    int pub;           // bit rho & 31: another chunk polls the row's result: it is published with a strong store
+    int arm;           // bit rho & 31: the row is polled in the other sweep: its record there is (re-)armed
+};
 
 // ---- compute warps -------------------------------------------------------------------------------
+// A lone warp per scheduler issues in order: a dependent DFMA chain overlaps with other work only if that
+// work sits BETWEEN the DFMAs of the same basic block.  So the step proper is one branch-free block -- the
+// neighbours' values, the next step's loads (block values, dependency codes -> addresses by arithmetic,
+// no branches), the chain, the ring store -- and everything that may loop (the barrier waits) is in front.
 template <int B, int S, bool ILU0, bool UPPER>
 __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem, int g0, int ns, int warp, int lane)
 {
     constexpr bool DINV = !(ILU0 && !UPPER);
-    using T = TwCfg<B, S, DINV>;
+    using T = TwCfg<B, S, DINV, UPPER>;
+    using Step = TwStep<B, S, T::NP>;
     constexpr int NS = T::kStages;
     const int rw = lane / B, r = lane - rw * B;
     const bool lane_ok = rw < T::RPW;
     const int rho = lane_ok ? warp * T::RPW + rw : 0; // idle lanes shadow row 0 of the step: computed, never stored
     const int src0 = lane_ok ? rw * B : 0;            // first lane of this row
     const unsigned smem_s = smem_u32(smem);
-    const unsigned ring_s = smem_s + T::kRingOff, zero_s = smem_s + T::kZeroOff;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
+    const unsigned ring_s = smem_s + T::kRingOff;
+    unsigned long long* data_bar = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
+    unsigned long long* ext_bar = data_bar + NS;
     volatile int* ctl = reinterpret_cast<volatile int*>(smem + T::kCtlOff);
     double* out = UPPER ? a.vpoll : a.tmp;
+    double* arm = UPPER ? a.tmp : a.vpoll;
     const double sent = sentinel();
+    const bool zero_ghosts = !UPPER && ILU0 && a.ghost_zero;
+    // per-lane constants of the look-ahead
+    const unsigned code_o = T::kCodeOff + (unsigned)rho * 4;
+    const unsigned val_o = T::kValOff + (unsigned)(warp * T::NP * 32 + lane) * 16;
+    const unsigned in_o = T::kRhsOff + (unsigned)(UPPER ? rho * T::W + r : r * T::RP + rho) * 8;
+    const unsigned pub_o = T::kPubOff + (unsigned)(rho >> 5) * 4, arm_o = T::kArmOff + (unsigned)(rho >> 5) * 4;
+    TWP_DECL;
 
-    for (int t = 0; t < ns; ++t) {
-        const int g = g0 + t, st = g % NS;
+    // everything about the step in stage `st` that does not depend on the steps before it: loads and
+    // arithmetic only.  Harmless on a stage that holds no step yet (the addresses are masked into range).
+    auto look_ahead = [&](int st, Step& N) {
         const unsigned sb = smem_s + (unsigned)st * T::kStageBytes;
-        mbar_wait(full + st, (unsigned)(g / NS) & 1u);
-        const int q0 = lds_s32(sb + T::kHdrOff), count = lds_s32(sb + T::kHdrOff + 4);
-        const bool active = lane_ok && rho < count;
-        const int q = q0 + rho;
-        // all shared-memory loads of the step issue back to back ahead of the one dependent DFMA chain
+        N.q0 = lds_s32(sb + T::kHdrOff);
+        N.count = lds_s32(sb + T::kHdrOff + 4);
+        N.flags = lds_s32(sb + T::kHdrOff + 12);
+        N.pub = lds_s32(sb + pub_o);
+        N.arm = lds_s32(sb + arm_o);
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            // kTwRing + index: the chunk's ring (index RING = the zero record behind it: "no dependency");
+            // else: slot of the stage's external values
+            const int c = lds_s32(sb + code_o + (unsigned)(s * T::RP) * 4);
+            N.xaddr[s] = ((c & kTwRing) ? ring_s : sb + T::kExtValOff) + (unsigned)(c & (2 * T::RING - 1)) * 32;
+        }
+    };
+
+    int st = g0 % NS;
+    unsigned par = (unsigned)(g0 / NS) & 1u;
+    Step SA, SB;
+    mbar_wait(data_bar + st, par);
+    look_ahead(st, SA);
+    TWP_MARK(7);
+
+    auto step = [&](int t, const Step& C, Step& N) {
+        const int g = g0 + t;
+        int st1 = st + 1;
+        unsigned par1 = par;
+        if (st1 == NS) {
+            st1 = 0;
+            par1 ^= 1u;
+        }
+        // ---- what may loop first ------------------------------------------------------------------
+        // (both tests issue back to back: a test of a completed phase takes ~90 cycles.  Never test a phase that
+        // will not complete -- the last step's "next stage": the test blocks until it times out)
+        const bool ok1 = t + 1 < ns ? mbar_try_wait(data_bar + st1, par1) : true; // the next step's record: landed long ago, normally
+        const bool ok0 = mbar_try_wait(ext_bar + st, par);    // this step's right-hand side and externals are parked
+        if (!ok0)
+            mbar_wait(ext_bar + st, par);
+        if (!ok1)
+            mbar_wait(data_bar + st1, par1);
+        TWP_MARK(t < 8 ? 6 : 0);
+        // ---- the step proper: one basic block ------------------------------------------------------
         double x[S][B];
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            const int c = lds_s32(sb + T::kCodeOff + (unsigned)(s * T::RP + rho) * 4);
-            const unsigned addr = c < 0 ? zero_s
-                                        : ((c & kTwRing) ? ring_s + (unsigned)(c & (T::RING - 1)) * 32
-                                                         : sb + T::kExtValOff + (unsigned)(c & (kTwMaxExt - 1)) * 32);
             if constexpr (B == 1) {
-                x[s][0] = lds_f64(addr);
+                x[s][0] = lds_f64(C.xaddr[s]);
             } else {
-                lds_v2(addr, x[s][0], x[s][1]);
+                lds_v2(C.xaddr[s], x[s][0], x[s][1]);
                 if constexpr (B == 3)
-                    x[s][2] = lds_f64(addr + 16);
+                    x[s][2] = lds_f64(C.xaddr[s] + 16);
                 if constexpr (B == 4)
-                    lds_v2(addr + 16, x[s][2], x[s][B - 1]);
+                    lds_v2(C.xaddr[s] + 16, x[s][2], x[s][B - 1]);
             }
         }
+        // this lane's block values (+ Dinv) and right-hand side: the record landed a step ago at the latest
+        const unsigned sb0 = smem_s + (unsigned)st * T::kStageBytes;
         double av[2 * T::NP];
 #pragma unroll
         for (int k = 0; k < T::NP; ++k)
-            lds_v2(sb + T::kValOff + (unsigned)((warp * T::NP + k) * 32 + lane) * 16, av[2 * k], av[2 * k + 1]);
-        const double in = lds_f64(sb + T::kRhsOff + (unsigned)(rho * T::W + r) * 8);
-
-        // ---- the row: same blocks, same order of operations as sweep_kernel ----------------------
+            lds_v2(sb0 + val_o + (unsigned)k * 512, av[2 * k], av[2 * k + 1]);
+        double in = lds_f64(sb0 + in_o);
+        in = (zero_ghosts && (C.flags & 1)) ? 0.0 : in; // ParallelOverlappingILU0 never touches ghost rows
+        look_ahead(st1, N);
+        // the row: same blocks, same order of operations as sweep_kernel
         double tsum = (UPPER && !ILU0) ? 0.0 : in;
 #pragma unroll
         for (int s = 0; s < S; ++s)
@@ -191,154 +305,264 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
             res = tsum; // ILU0 lower: L_ii = I
         }
         res = guard(res);
-        if (active) {
+        const bool active = lane_ok && rho < C.count;
+        const int q = C.q0 + rho;
+        if (active)
             sts_f64(ring_s + (unsigned)(q & (T::RING - 1)) * 32 + r * 8, res);
-            st_relaxed(out + (size_t)q * T::W + r, res);
-            if (UPPER) {
-                a.v[VIDX(a.n, q, r)] = res;
-                st_relaxed(a.tmp + (size_t)q * T::W + r, sent); // re-arm for the next apply
-            } else {
-                st_relaxed(a.vpoll + (size_t)q * T::W + r, sent); // arm the upper sweep's records
-            }
-        }
-        named_bar_sync(1, T::NW * 32); // ring writes visible to the four warps; everybody is done with the stage
+        TWP_MARK(1);
+        named_bar_sync(1, T::NW * 32); // the ring writes are visible to the four warps; everybody is done with the stage
         if (threadIdx.x == 0)
-            ctl[0] = g + 1; // releases the stage to the loaders
+            ctl[kCtlReleased] = g + 1; // the stage may be refilled
+        TWP_MARK(2);
+        // Publish BEHIND the barrier, from the registers: a barrier waits for the L2's acknowledgement of the
+        // strong stores in front of it (+200 cycles per step, measured); here they travel while the next step
+        // waits for its externals.  Only rows another chunk polls get a strong store (and only those have a
+        // sentinel to arm): the rest of y is read by the upper sweep (a later kernel), the rest of the upper
+        // sweep's records by nobody.  (Deferring the weak stores into the next step's block was measured: no gain --
+        // a lone warp per scheduler is bound by its instruction count, ~5 cycles per instruction, not by the chain.)
+        if (active && !TW_DBG(1)) {
+            const bool polled = (C.pub >> (rho & 31)) & 1;
+            if (UPPER) {
+                if (polled)
+                    st_relaxed(out + (size_t)q * T::W + r, res);
+                a.v[VIDX(a.n, q, r)] = res;
+            } else {
+                if (polled)
+                    st_relaxed(out + (size_t)q * T::W + r, res);
+                else
+                    out[(size_t)q * T::W + r] = res;
+            }
+            if ((C.arm >> (rho & 31)) & 1)
+                arm[(size_t)q * T::W + r] = sent; // lower: arm the upper sweep's records; upper: re-arm for the next apply
+        }
+        TWP_MARK(3);
+        st = st1;
+        par = par1;
+    };
+
+    for (int t = 0; t < ns; t += 2) {
+        step(t, SA, SB);
+        if (t + 1 < ns)
+            step(t + 1, SB, SA);
     }
+    TWP_FLUSH(0, warp == 0 && lane == 0);
+    TWP_COUNT(24, warp == 0 && lane == 0, ns);
+    TWP_COUNT(25, warp == 0 && lane == 0, 1);
 }
 
-// ---- loader warp: one TMA bulk copy per step + the right-hand side -------------------------------------
+// ---- loader warp: ONE TMA bulk copy of the step's record per step, completion on the stage's "data" mbarrier ----
 template <int B, int S, bool ILU0, bool UPPER>
 __device__ __forceinline__ void tw_loader(const TwArgs& a, unsigned char* smem, int rec0, int g0, int ns, int lane)
 {
     constexpr bool DINV = !(ILU0 && !UPPER);
-    using T = TwCfg<B, S, DINV>;
+    using T = TwCfg<B, S, DINV, UPPER>;
     constexpr int NS = T::kStages;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
+    unsigned long long* data_bar = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
     volatile int* ctl = reinterpret_cast<volatile int*>(smem + T::kCtlOff);
+    const int PF = a.prefetch;
+    // the chunk's right-hand side is a contiguous range of positions: pull all of it into the L2 now (a
+    // few tens of KB), the step records in batches a few steps ahead of the copies into shared memory --
+    // a stage filled from HBM takes ~1.5 us, kStages of them in flight would cap a step at ~500 cycles
+    if (!TW_DBG(16)) {
+        const int qa = ctl[kCtlQ0], qb = ctl[kCtlQ1];
+        if (UPPER) {
+            if (lane == 0)
+                l2_prefetch_bulk(a.tmp + (size_t)qa * T::W, (unsigned)(qb - qa) * T::W * 8);
+        } else if (lane < B) {
+            l2_prefetch_bulk(a.d + VIDX(a.n, qa, lane), (unsigned)(qb - qa) * 8);
+        }
+        if (lane == 0 && PF > 0)
+            l2_prefetch_bulk(a.stream + (size_t)rec0 * T::kRecBytes, (unsigned)(min(PF + NS, ns) * T::kRecBytes));
+    }
+    if (lane != 0)
+        return;
+    TWP_DECL;
     const unsigned char* rec = a.stream + (size_t)rec0 * T::kRecBytes;
     for (int t = 0; t < ns; ++t, rec += T::kRecBytes) {
         const int g = g0 + t, st = g % NS;
-        unsigned char* sb = smem + (size_t)st * T::kStageBytes;
-        const int4 hdr = __ldg(reinterpret_cast<const int4*>(rec)); // q0, count, n_ext, flags
-        while (ctl[0] < g + 1 - NS)
-            __nanosleep(20);
-        if (lane == 0) {
-            mbar_expect_tx(full + st, (unsigned)T::kRecBytes + (UPPER ? (unsigned)hdr.y * T::W * 8 : 0u));
-            tma_load_1d(sb, rec, (unsigned)T::kRecBytes, full + st);
-            if (UPPER) // y_i of the lower sweep (complete: previous kernel)
-                tma_load_1d(sb + T::kRhsOff, a.tmp + (size_t)hdr.x * T::W, (unsigned)hdr.y * T::W * 8, full + st);
-        }
-        if (!UPPER) {
-            const bool ghost = ILU0 && (hdr.w & 1); // ParallelOverlappingILU0 never touches ghost rows
-            const unsigned rhs_s = smem_u32(sb + T::kRhsOff);
-            if (ghost && a.ghost_zero) {
-                for (int e = lane; e < hdr.y * T::W; e += 32)
-                    sts_f64(rhs_s + e * 8, 0.0);
-                mbar_arrive(full + st);
-            } else {
-                const double* src = ghost ? a.v : a.d;
-#pragma unroll
-                for (int c = 0; c < B; ++c)
-                    for (int rho = lane; rho < hdr.y; rho += 32)
-                        cp_async8(rhs_s + (unsigned)(rho * T::W + c) * 8, src + VIDX(a.n, hdr.x + rho, c));
-                cp_async_arrive_noinc(full + st);
-            }
-        }
+        if (PF > 0 && (t & 3) == 0 && t + NS + PF < ns && !TW_DBG(16)) // four records per prefetch
+            l2_prefetch_bulk(rec + (size_t)(NS + PF) * T::kRecBytes, (unsigned)(min(4, ns - t - NS - PF) * T::kRecBytes));
+        TWP_MARK(0);
+        while (ctl[kCtlReleased] < g + 1 - NS) {} // plain spin (a __nanosleep would cost a microsecond)
+        TWP_MARK(1);
+        const unsigned bytes = TW_DBG(4) ? 48u : (unsigned)T::kRecBytes; // timing experiment: header only
+        mbar_expect_tx(data_bar + st, bytes);
+        tma_load_1d(smem + (size_t)st * T::kStageBytes, rec, bytes, data_bar + st);
+        TWP_MARK(2);
     }
+    TWP_FLUSH(8, true);
 }
 
 // ---- poll warps: the dependencies the chunk's ring does not serve ---------------------------------------
 template <int B, int S, bool ILU0, bool UPPER>
-__device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, int rec0, int g0, int ns, int pw, int lane)
+__device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, int rec0, int g0, int ns, int pw, int npw, int lane)
 {
     constexpr bool DINV = !(ILU0 && !UPPER);
-    using T = TwCfg<B, S, DINV>;
+    using T = TwCfg<B, S, DINV, UPPER>;
     constexpr int NS = T::kStages;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
+    unsigned long long* ext_bar = reinterpret_cast<unsigned long long*>(smem + T::kBarOff) + NS;
     volatile int* ctl = reinterpret_cast<volatile int*>(smem + T::kCtlOff);
     const double* out = UPPER ? a.vpoll : a.tmp;
-    for (int t = pw; t < ns; t += kTwPollWarps) {
-        const unsigned char* rec = a.stream + (size_t)(rec0 + t) * T::kRecBytes;
+    const unsigned char* rec = a.stream + (size_t)(rec0 + pw) * T::kRecBytes;
+    constexpr int NR = (T::R + 31) / 32;      // rows per lane
+    constexpr int NC = UPPER ? T::W : B;      // right-hand side words per row
+    // A round trip to the L2 is 1-3 thousand cycles under load and a warp serves every npw-th step.  So the
+    // header and external list of this warp's step after next, and the right-hand side plus a first SAMPLE of the
+    // dependencies of its next step travel while this step is served (a sample that finds the sentinel is repeated).
+    auto load_head = [&](const unsigned char* r, int4& hdr, int& pos) {
+        hdr = __ldg(reinterpret_cast<const int4*>(r)); // q0, count, n_ext, flags
+        pos = __ldg(reinterpret_cast<const int*>(r + T::kExtPosOff) + lane);
+    };
+    auto load_rhs = [&](const int4& hdr, double (&rhs)[NR][NC]) {
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int rho = lane + 32 * i;
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                rhs[i][c] = 0.0;
+            if (rho < hdr.y && !TW_DBG(8)) {
+                if constexpr (UPPER) { // y_i of the lower sweep (complete: previous kernel)
+                    const double2* p = reinterpret_cast<const double2*>(a.tmp + (size_t)(hdr.x + rho) * T::W);
+                    const double2 u0 = __ldcs(p);
+                    rhs[i][0] = u0.x;
+                    rhs[i][1] = u0.y;
+                    if constexpr (T::W == 4) {
+                        const double2 u1 = __ldcs(p + 1);
+                        rhs[i][2] = u1.x;
+                        rhs[i][NC - 1] = u1.y;
+                    }
+                } else { // ParallelOverlappingILU0 never touches ghost rows: they keep v's input (or enter as 0)
+                    const double* src = (ILU0 && (hdr.w & 1)) ? a.v : a.d;
+#pragma unroll
+                    for (int c = 0; c < B; ++c)
+                        rhs[i][c] = __ldcs(src + VIDX(a.n, hdr.x + rho, c));
+                }
+            }
+        }
+    };
+    int4 hdr = make_int4(0, 0, 0, 0), hdr1 = hdr, hdr2 = hdr;
+    int pos = -1, pos1 = -1, pos2 = -1;
+    double rhs[NR][NC], rhs1[NR][NC], x[B], x1[B];
+    if (pw < ns) {
+        load_head(rec, hdr, pos);
+        load_rhs(hdr, rhs);
+        if (pos >= 0)
+            rec_load_strong<B>(out, (size_t)pos, x);
+    }
+    if (pw + npw < ns)
+        load_head(rec + (size_t)npw * T::kRecBytes, hdr1, pos1);
+    TWP_DECL;
+    for (int t = pw; t < ns; t += npw, rec += (size_t)npw * T::kRecBytes) {
         const int g = g0 + t, st = g % NS;
-        const int n_ext = __ldg(reinterpret_cast<const int*>(rec) + 2);
-        const int pos = lane < n_ext ? __ldg(reinterpret_cast<const int*>(rec + T::kExtPosOff) + lane) : -1;
-        double x[B];
+        if (t + 2 * npw < ns)
+            load_head(rec + (size_t)2 * npw * T::kRecBytes, hdr2, pos2);
+        if (t + npw < ns) { // the next step this warp serves
+            load_rhs(hdr1, rhs1);
+            if (pos1 >= 0)
+                rec_load_strong<B>(out, (size_t)pos1, x1);
+        }
+        TWP_MARK(0);
         if (pos >= 0) {
             int tries = 0;
-            do { // one strong vector load per round trip; every word validates itself against the sentinel
-                if (++tries > 8)
-                    __nanosleep(40);
+            while (!rec_valid<B>(x) && !TW_DBG(2)) { // every word validates itself against the sentinel
+                if (++tries > 64) // far from the front (chunk start): stay off the L2
+                    __nanosleep(200);
                 rec_load_strong<B>(out, (size_t)pos, x);
-            } while (!rec_valid<B>(x));
+            }
+            TWP_COUNT(26, lane == 0 && pw == 0, tries);
         }
-        while (ctl[0] < g + 1 - NS)
-            __nanosleep(20);
+        __syncwarp();
+        TWP_MARK(1);
+        while (ctl[kCtlReleased] < g + 1 - NS) {}
+        TWP_MARK(2);
+        const unsigned sb = smem_u32(smem + (size_t)st * T::kStageBytes);
         if (pos >= 0) {
-            const unsigned dst = smem_u32(smem + (size_t)st * T::kStageBytes + T::kExtValOff) + lane * 32;
 #pragma unroll
             for (int c = 0; c < B; ++c)
-                sts_f64(dst + c * 8, x[c]);
+                sts_f64(sb + T::kExtValOff + lane * 32 + c * 8, x[c]);
+        }
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            const int rho = lane + 32 * i;
+            if (rho < T::RP) {
+#pragma unroll
+                for (int c = 0; c < NC; ++c)
+                    sts_f64(sb + T::kRhsOff + (unsigned)(UPPER ? rho * T::W + c : c * T::RP + rho) * 8, rhs[i][c]);
+            }
         }
         __syncwarp();
         if (lane == 0)
-            mbar_arrive(full + st); // release: the stores above are visible to whoever passes the barrier
+            mbar_arrive(ext_bar + st); // release: the stores above are visible to whoever passes the barrier
+        TWP_MARK(3);
+        hdr1 = hdr2;
+        pos = pos1;
+        pos1 = pos2;
+        pos2 = -1;
+#pragma unroll
+        for (int c = 0; c < B; ++c)
+            x[c] = x1[c];
+#pragma unroll
+        for (int i = 0; i < NR; ++i)
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                rhs[i][c] = rhs1[i][c];
     }
+    TWP_FLUSH(16, lane == 0 && pw == 0);
 }
 
 template <int B, int S, bool ILU0, bool UPPER>
-__global__ void __launch_bounds__(kTwThreads, 2) tw_sweep_kernel(TwArgs a)
+__global__ void __launch_bounds__(kTwMaxThreads, 2) tw_sweep_kernel(TwArgs a)
 {
     constexpr bool DINV = !(ILU0 && !UPPER);
-    using T = TwCfg<B, S, DINV>;
+    using T = TwCfg<B, S, DINV, UPPER>;
     extern __shared__ __align__(128) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
     volatile int* ctl = reinterpret_cast<volatile int*>(smem + T::kCtlOff);
     if (threadIdx.x == 0) {
-        // arrivals per stage: the loader's expect_tx, the poll warp, and (lower) the loader lanes' cp.async
-        for (int i = 0; i < T::kStages; ++i)
-            mbar_init(full + i, UPPER ? 2u : 34u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < 4; ++i) {
-            reinterpret_cast<double*>(smem + T::kZeroOff)[i] = 0.0;
-            ctl[i] = 0;
+        for (int i = 0; i < T::kStages; ++i) {
+            mbar_init(bars + i, 1u);                // data: the loader's expect_tx
+            mbar_init(bars + T::kStages + i, 1u);   // ext: the poll warp
         }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int i = 0; i < 8; ++i)
+            ctl[i] = 0;
     }
-    // idle lanes and rows beyond a step's count read ring / rhs words nobody wrote: keep them finite
-    for (int i = threadIdx.x; i < (T::kZeroOff - T::kRingOff) / 8; i += blockDim.x)
-        reinterpret_cast<double*>(smem + T::kRingOff)[i] = 0.0;
-    for (int st = 0; st < T::kStages; ++st)
-        for (int i = threadIdx.x; i < (T::kStageBytes - T::kRhsOff) / 8; i += blockDim.x)
-            reinterpret_cast<double*>(smem + (size_t)st * T::kStageBytes + T::kRhsOff)[i] = 0.0;
+    // idle lanes, rows beyond a step's count and the look-ahead behind a chunk's last step read words nobody
+    // wrote: all-zero stages decode to in-range addresses and finite values
+    for (int i = threadIdx.x; i < T::kBarOff / 16; i += blockDim.x)
+        reinterpret_cast<int4*>(smem)[i] = make_int4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes before the TMA writes
     __syncthreads();
     const bool skip = a.check_done && a.sc->done;
+    const int npw = a.poll_warps;
     int g = 0; // steps walked by this CTA so far: stage = g % kStages, phase = (g / kStages) & 1
     for (;;) {
         if (threadIdx.x == 0) {
             const unsigned int tk = atomicAdd(a.ticket.next, 1u);
             if (skip || tk >= (unsigned)a.nchunks) {
-                ctl[3] = 1;
+                ctl[kCtlStop] = 1;
             } else {
                 const int c = UPPER ? a.nchunks - 1 - (int)tk : (int)tk;
                 const int s0 = a.chunk_step0[c], s1 = a.chunk_step0[c + 1];
-                ctl[1] = UPPER ? a.nsteps - s1 : s0; // first record of the chunk in walking order
-                ctl[2] = s1 - s0;
+                ctl[kCtlRec0] = UPPER ? a.nsteps - s1 : s0; // first record of the chunk in walking order
+                ctl[kCtlSteps] = s1 - s0;
+                ctl[kCtlQ0] = a.step_q0[s0]; // the chunk's positions
+                ctl[kCtlQ1] = a.step_q0[s1];
             }
         }
         __syncthreads();
-        if (ctl[3])
+        if (ctl[kCtlStop])
             break;
-        const int rec0 = ctl[1], ns = ctl[2];
+        const int rec0 = ctl[kCtlRec0], ns = ctl[kCtlSteps];
         if (warp < T::NW)
             tw_compute<B, S, ILU0, UPPER>(a, smem, g, ns, warp, lane);
         else if (warp == T::NW)
             tw_loader<B, S, ILU0, UPPER>(a, smem, rec0, g, ns, lane);
         else
-            tw_poller<B, S, ILU0, UPPER>(a, smem, rec0, g, ns, warp - T::NW - 1, lane);
+            tw_poller<B, S, ILU0, UPPER>(a, smem, rec0, g, ns, warp - T::NW - 1, npw, lane);
         g += ns;
-        __syncthreads(); // everybody has read ctl[1..2]; the chunk is finished
+        __syncthreads(); // everybody has read the control words; the chunk is finished and published
     }
     return_ticket(a.ticket);
 }
@@ -351,7 +575,7 @@ __global__ void __launch_bounds__(256) tw_fill_kernel(int nsteps, int upper, con
                                                       const double* __restrict__ M, const double* __restrict__ dinv,
                                                       unsigned char* __restrict__ stream)
 {
-    using T = TwCfg<B, S, DINV>;
+    using T = TwCfg<B, S, DINV, true>; // the record layout does not depend on the direction
     constexpr int BB = B * B;
     const int64_t total = (int64_t)nsteps * T::NW * 32;
     for (int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; tid < total; tid += (int64_t)gridDim.x * blockDim.x) {

@@ -78,7 +78,7 @@ def replay_dilu(A, Dinv, d, n_interior=None, **kw):
                     for k in range(S):
                         code = P["codes"][st, k, rho]
                         if k >= len(ents):
-                            assert code == -1
+                            assert code == RING | ring_n  # "no dependency": the zero record behind the ring
                             continue
                         if code & RING:
                             x = ring[code & (ring_n - 1)]
