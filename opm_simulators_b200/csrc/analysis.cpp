@@ -316,7 +316,9 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
     const int max_slots = b >= 3 ? 4 : 3; // instantiated tile walkers (solver.cu, DISPATCH_BS)
     if (schedule_mode != 0 && (max_wl > max_slots || max_wu > max_slots || n >= (int64_t)kTwExt))
         schedule_mode = 0;
-    const int R = kTwWarps * (32 / b); // rows of one CTA step
+    // rows of one CTA step: the tile walkers take kTwWarps * (32 / b), but a step is also one slice of the SELL
+    // layout the SpMV and the factorisation kernels work on, so no more than a slice
+    const int R = std::min(kTwWarps * (32 / b), kSlice);
     int32_t nlev = 0;
     for (int64_t i = 0; i < n; ++i)
         nlev = std::max(nlev, lev[i] + 1);
@@ -448,13 +450,13 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
     // before the first row of a step (behind its last row, upper sweep) is intact.
     int tw_window = 0;
     if (schedule_mode == 1) {
-        L.tw_rows = R;
+        L.tw_rows = kTwWarps * (32 / b); // what the kernels' record layout provides for
         L.tw_ring = 256;
-        while (L.tw_ring < 4 * R)
+        while (L.tw_ring < 4 * L.tw_rows)
             L.tw_ring *= 2;
         L.tw_slots[0] = std::max(3, max_wl);
         L.tw_slots[1] = std::max(3, max_wu);
-        tw_window = L.tw_ring - 2 * R;
+        tw_window = L.tw_ring - 2 * L.tw_rows;
         auto n_ext = [&](int64_t i, bool upper) {
             if (i >= n_interior)
                 return 0;
@@ -589,6 +591,29 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
                 slot_of_native[k] = (int32_t)g;
             }
         }
+    }
+
+    // ---- mode 1: the order in which the factorisation kernels take the slices ---------------------
+    // They run one warp per slice with an in-order ticket.  In (chunk, step) order consecutive slices depend
+    // on each other and only a few chunks would be in flight; ordered by the level of a slice in the slice
+    // dependency graph they sweep the whole front at once, like the level schedule does.
+    L.factor_order.clear();
+    if (schedule_mode == 1) {
+        std::vector<int32_t> slice_of(n), slev(L.n_slices, 0);
+        for (int sl = 0; sl < L.n_slices; ++sl)
+            for (int32_t q = L.slice_q0[sl]; q < L.slice_q0[sl + 1]; ++q)
+                slice_of[q] = sl;
+        for (int sl = 0; sl < L.n_slices; ++sl) // dependencies point to earlier slices
+            for (int32_t q = L.slice_q0[sl]; q < L.slice_q0[sl + 1]; ++q) {
+                const int64_t i = L.r2n[q];
+                if (i >= n_interior)
+                    continue;
+                for (int64_t k = rowptr[i]; k < diag[i]; ++k)
+                    slev[sl] = std::max(slev[sl], slev[slice_of[L.n2r[col[k]]]] + 1);
+            }
+        L.factor_order.resize(L.n_slices);
+        std::iota(L.factor_order.begin(), L.factor_order.end(), 0);
+        std::stable_sort(L.factor_order.begin(), L.factor_order.end(), [&](int32_t x, int32_t y) { return slev[x] < slev[y]; });
     }
 
     // ---- mode 1: dependency codes, external lists and block slots of every step -------------------

@@ -832,6 +832,7 @@ __device__ __forceinline__ void return_ticket(const Ticket& t)
 struct FactorArgs {
     int nslices;
     const SliceMeta* slices;
+    const int* order;       // ticket k works on slice order[k] (nullptr: k)
     const int* slot_col;
     const double* A;        // DILU: matrix values ; ILU0: unused
     double* F;              // ILU0: factor values, updated in place
@@ -865,8 +866,9 @@ __global__ void __launch_bounds__(kCtaThreads) dilu_factor_kernel(FactorArgs a)
     constexpr int BB = B * B;
     const unsigned int chunk = take_ticket(a.ticket);
     const int lane = threadIdx.x & 31;
-    const int S = (int)chunk * kWarpsPerCta + (threadIdx.x >> 5);
-    if (S < a.nslices) {
+    const int T = (int)chunk * kWarpsPerCta + (threadIdx.x >> 5);
+    if (T < a.nslices) {
+        const int S = a.order ? a.order[T] : T;
         const SliceMeta m = a.slices[S];
         if (lane < m.count) {
             const int q = m.q0 + lane;
@@ -970,8 +972,9 @@ __global__ void __launch_bounds__(kCtaThreads) ilu0_factor_kernel(FactorArgs a)
     constexpr int BB = B * B;
     const unsigned int chunk = take_ticket(a.ticket);
     const int lane = threadIdx.x & 31;
-    const int S = (int)chunk * kWarpsPerCta + (threadIdx.x >> 5);
-    if (S < a.nslices) {
+    const int T = (int)chunk * kWarpsPerCta + (threadIdx.x >> 5);
+    if (T < a.nslices) {
+        const int S = a.order ? a.order[T] : T;
         const SliceMeta m = a.slices[S];
         {   // pull this slice's blocks (one contiguous region) into the L2 while the warp waits
             const char* region = reinterpret_cast<const char*>(a.F + (size_t)m.base * 32 * BB);

@@ -75,6 +75,7 @@ struct Layout {
     int n_steps = 0;
     std::vector<int32_t> step_q0;     // [n_steps+1]
     std::vector<int32_t> chunk_step0; // [n_chunks+1]
+    std::vector<int32_t> factor_order; // [n_slices] the factorisation kernels' ticket k works on slice factor_order[k]
     std::vector<int32_t> step_flags;  // [n_steps] bit 0: the step's rows are ghost rows
     // per direction d (0 lower, 1 upper), by step s (NOT in walking order):
     //   tw_code[d][(s*S + k)*RP + rho]: where row rho of the step finds dependency k:

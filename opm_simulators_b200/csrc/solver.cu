@@ -119,11 +119,12 @@ struct opmb200_solver {
     int verbosity = 0;
     int op_repeats = 1;
     int throttle = 6;
-    int schedule = 0;   // requested: 0 levels, 1 tiles, 2 auto (what was built: L.schedule_mode)
+    int schedule = 2;   // requested: 0 levels, 1 tiles, 2 auto (what was built: L.schedule_mode)
     int chunk_rows = 0; // > 0 contiguous chunks, 0 automatic, < 0 a tile shape
-    int prefetch = 12;  // tile walkers: L2 look-ahead of the loader warp, in steps (<= 32)
-    int poll_warps = 3; // tile walkers: warps polling the dependencies that cross a chunk boundary (1..3)
+    int prefetch = 4;   // tile walkers: L2 look-ahead of the loader warp, in steps (<= 32)
+    int poll_warps = 4; // tile walkers: warps polling the dependencies that cross a chunk boundary (1..6)
     int debug = 0;      // OPMB200_TWDBG builds: timing experiments (wrong results)
+    int ctas_per_sm = 1; // tile walkers: persistent CTAs per SM (1 or 2)
     int device = 0;
     int num_sms = 148;
     cudaStream_t stream = nullptr;
@@ -133,7 +134,7 @@ struct opmb200_solver {
 
     DevBuf<SliceMeta> slices;
     DevBuf<int> slot_col, slot_src, row_static, r2n, n2r, level_q0, l_transpose, trip_ptr, trip_src, trip_dst, row_flag;
-    DevBuf<int> chunk_step0, step_q0, tw_slot[2]; // schedule "tiles": step tables of the tile walkers
+    DevBuf<int> chunk_step0, step_q0, tw_slot[2], factor_order; // schedule "tiles": step tables of the tile walkers
     DevBuf<double> A, F, dinv, dinv_rec, vals_native;
     DevBuf<unsigned char> tw_stream[2]; // schedule "tiles": step records of the lower / upper sweep
     DevBuf<double> vx, vr, vp, vv, vt, vy, vrt, vw, nat0, nat1;
@@ -399,7 +400,7 @@ int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
         c.ticket = a.ticket;
         c.sc = a.sc;
         c.check_done = a.check_done;
-        const int cgrid = std::max(1, std::min(s->L.n_chunks, 2 * s->num_sms));
+        const int cgrid = std::max(1, std::min(s->L.n_chunks, s->ctas_per_sm * s->num_sms));
         const bool ilu0 = s->prec == PREC_ILU0;
         DISPATCH_BS(s->b, s->L.tw_slots[upper ? 1 : 0], {
             if (ilu0) {
@@ -454,6 +455,7 @@ int prec_update(opmb200_solver* s)
     FactorArgs a;
     a.nslices = s->L.n_slices;
     a.slices = s->slices.p;
+    a.order = s->L.schedule_mode == 1 ? s->factor_order.p : nullptr;
     a.slot_col = s->slot_col.p;
     a.A = s->A.p;
     a.F = s->F.p;
@@ -569,14 +571,15 @@ int parse_options(opmb200_solver* s, const char* json)
         s->relaxation = prm.get<double>("preconditioner.relaxation", 1.0);
         s->op_repeats = prm.get<int>("b200.operator_repeats", 1);
         s->throttle = prm.get<int>("b200.throttle_levels", 6);
-        const std::string sched = prm.get<std::string>("b200.schedule", "levels");
+        const std::string sched = prm.get<std::string>("b200.schedule", "auto");
         if (sched != "levels" && sched != "tiles" && sched != "chunks" && sched != "auto")
             return fail(OPMB200_BAD_OPTIONS, "b200.schedule must be \"levels\", \"tiles\" or \"auto\"");
         s->schedule = sched == "levels" ? 0 : (sched == "auto" ? 2 : 1);
         s->chunk_rows = prm.get<int>("b200.chunk_rows", 0);
-        s->prefetch = std::max(0, std::min(32, prm.get<int>("b200.prefetch_steps", 12)));
-        s->poll_warps = std::max(1, std::min(kTwMaxPollWarps, prm.get<int>("b200.poll_warps", 3)));
+        s->prefetch = std::max(0, std::min(32, prm.get<int>("b200.prefetch_steps", 4)));
+        s->poll_warps = std::max(1, std::min(kTwMaxPollWarps, prm.get<int>("b200.poll_warps", 4)));
         s->debug = prm.get<int>("b200.debug_timing", 0);
+        s->ctas_per_sm = std::max(1, std::min(2, prm.get<int>("b200.ctas_per_sm", 1)));
         s->use_graph = prm.get<int>("b200.cuda_graph", 1) != 0;
         s->trace = std::getenv("OPMB200_TRACE") != nullptr;
     } catch (const std::exception& e) {
@@ -1032,6 +1035,7 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
             CUDA_TRY(s->tw_slot[up].upload(L.tw_slot[up], st));
         }
         CUDA_TRY(s->step_q0.upload(L.step_q0, st));
+        CUDA_TRY(s->factor_order.upload(L.factor_order, st));
         CUDA_TRY(s->chunk_step0.upload(L.chunk_step0, st));
         DISPATCH_BS(block_size, L.tw_slots[0], {
             CUDA_TRY(cudaFuncSetAttribute(tw_sweep_kernel<B, S, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

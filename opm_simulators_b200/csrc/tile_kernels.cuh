@@ -28,8 +28,9 @@
 
 namespace opmb200 {
 
-constexpr int kTwMaxPollWarps = 3;
-// launch bound (8 warps: 128 registers per thread with two CTAs per SM); the launch picks the poll warps
+constexpr int kTwMaxPollWarps = 6;
+// launch bound; the launch picks the poll warps.  ONE CTA per SM: two co-resident tile walkers slow each other
+// down by more than they gain (C3: 250 us with two per SM, 205 us with one -- measured)
 constexpr int kTwMaxThreads = (kTwWarps + 1 + kTwMaxPollWarps) * 32;
 
 template <int B, int S, bool DINV, bool UPPER>
@@ -56,8 +57,8 @@ struct TwCfg {
     static constexpr int kRhsBytes = UPPER ? RP * W * 8 : B * RP * 8;
     static constexpr int kExtValOff = kRhsOff + kRhsBytes;           // [kTwMaxExt][4] doubles
     static constexpr int kStageBytes = (kExtValOff + kTwMaxExt * 32 + 127) & ~127;
-    // stages: what fits in ~96 KB (two CTAs per SM)
-    static constexpr int kStagesRaw = 98304 / kStageBytes;
+    // stages: what fits in ~128 KB
+    static constexpr int kStagesRaw = 131072 / kStageBytes;
     static constexpr int kStages = kStagesRaw < 2 ? 2 : (kStagesRaw > 8 ? 8 : kStagesRaw);
     static constexpr int kRingOff = kStages * kStageBytes;           // [RING][4] doubles
     static constexpr int kZeroOff = kRingOff + RING * 32;            // one all-zero record
@@ -464,9 +465,10 @@ __device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, 
         TWP_MARK(0);
         if (pos >= 0) {
             int tries = 0;
-            while (!rec_valid<B>(x) && !TW_DBG(2)) { // every word validates itself against the sentinel
-                if (++tries > 64) // far from the front (chunk start): stay off the L2
-                    __nanosleep(200);
+            // every word validates itself against the sentinel.  No nap between the samples, not even at chunk start:
+            // the first step's wait IS the hop from chunk to chunk, and a __nanosleep costs about a microsecond
+            while (!rec_valid<B>(x) && !TW_DBG(2)) {
+                ++tries;
                 rec_load_strong<B>(out, (size_t)pos, x);
             }
             TWP_COUNT(26, lane == 0 && pw == 0, tries);
@@ -511,7 +513,7 @@ __device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, 
 }
 
 template <int B, int S, bool ILU0, bool UPPER>
-__global__ void __launch_bounds__(kTwMaxThreads, 2) tw_sweep_kernel(TwArgs a)
+__global__ void __launch_bounds__(kTwMaxThreads, 1) tw_sweep_kernel(TwArgs a)
 {
     constexpr bool DINV = !(ILU0 && !UPPER);
     using T = TwCfg<B, S, DINV, UPPER>;
