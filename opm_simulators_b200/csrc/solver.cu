@@ -94,6 +94,8 @@ bool is_device_ptr(const void* p)
 }
 
 enum PrecKind { PREC_NONE = 0, PREC_DILU = 1, PREC_ILU0 = 2 };
+constexpr size_t kRegisterMinBytes = size_t(1) << 20; // small buffers are not worth a registration
+constexpr size_t kRegisterMax = 8;
 
 double sentinel_host()
 {
@@ -174,6 +176,13 @@ struct opmb200_solver {
     std::vector<std::pair<const char*, cudaEvent_t>> trace_ev;
     size_t trace_used = 0;
 
+    // caller buffers page-locked by the library (gpuistl/ISTLSolverGPUISTL.hpp:429-432, 275-278, 446-449 register the
+    // matrix, x and b the same way): Flow assembles into the same storage every Newton step, so each buffer is
+    // registered once and copied at pinned speed from then on; unregistered in the destructor
+    const double* last_values = nullptr; // device copy of the values of the last update (caller's or vals_native)
+    bool register_host = true;
+    std::vector<std::pair<const void*, size_t>> registered;
+
     double t_analysis_s = 0, t_update_ms = 0, t_solve_ms = 0;
     int64_t launches = 0;
     std::vector<double> last_hist;
@@ -182,6 +191,9 @@ struct opmb200_solver {
     {
         if (iter_graph)
             cudaGraphExecDestroy(iter_graph);
+        for (auto& r : registered)
+            if (cudaHostUnregister(const_cast<void*>(r.first)) != cudaSuccess)
+                cudaGetLastError(); // the caller may have freed the buffer already
         if (h_sc)
             cudaFreeHost(h_sc);
         if (h_small)
@@ -508,11 +520,38 @@ int relayout(opmb200_solver* s, const double* dev_vals)
     return check_launch(s, "relayout");
 }
 
+// page-lock a caller's host buffer the first time it is seen (no-op for device, pinned or small buffers)
+void ensure_registered(opmb200_solver* s, const void* p, size_t bytes)
+{
+    if (!s->register_host || !p || bytes < kRegisterMinBytes)
+        return;
+    for (auto& r : s->registered)
+        if (r.first == p && r.second >= bytes)
+            return;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    if (at.type != cudaMemoryTypeUnregistered)
+        return;
+    if (s->registered.size() >= kRegisterMax) { // a caller that keeps moving its storage: drop the oldest
+        if (cudaHostUnregister(const_cast<void*>(s->registered.front().first)) != cudaSuccess)
+            cudaGetLastError();
+        s->registered.erase(s->registered.begin());
+    }
+    if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterDefault) == cudaSuccess)
+        s->registered.emplace_back(p, bytes);
+    else
+        cudaGetLastError(); // stays pageable: the copy still works
+}
+
 // ---- staging helpers: caller vector (host or device, natural order) <-> level-ordered device vector
 int stage_in(opmb200_solver* s, const double* user, double* nat_tmp, double* lvl)
 {
     const double* src = user;
     if (!is_device_ptr(user)) {
+        ensure_registered(s, user, s->len() * sizeof(double));
         CUDA_TRY(cudaMemcpyAsync(nat_tmp, user, s->len() * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         src = nat_tmp;
     }
@@ -526,8 +565,10 @@ int stage_out(opmb200_solver* s, const double* lvl, double* nat_tmp, double* use
     double* dst = dev ? user : nat_tmp;
     DISPATCH_B(s->b, (permute_out_kernel<B><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, s->n2r.p, lvl, dst)));
     TRY(check_launch(s, "permute_out"));
-    if (!dev)
+    if (!dev) {
+        ensure_registered(s, user, s->len() * sizeof(double));
         CUDA_TRY(cudaMemcpyAsync(user, nat_tmp, s->len() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    }
     return OPMB200_SUCCESS;
 }
 
@@ -579,6 +620,7 @@ int parse_options(opmb200_solver* s, const char* json)
         s->prefetch = std::max(0, std::min(32, prm.get<int>("b200.prefetch_steps", 4)));
         s->poll_warps = std::max(1, std::min(kTwMaxPollWarps, prm.get<int>("b200.poll_warps", 4)));
         s->debug = prm.get<int>("b200.debug_timing", 0);
+        s->register_host = prm.get<int>("b200.register_host_buffers", 1) != 0;
         s->ctas_per_sm = std::max(1, std::min(2, prm.get<int>("b200.ctas_per_sm", 1)));
         s->use_graph = prm.get<int>("b200.cuda_graph", 1) != 0;
         s->trace = std::getenv("OPMB200_TRACE") != nullptr;
@@ -1147,10 +1189,12 @@ int opmb200_update_values(opmb200_solver* s, const double* values)
     CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
     const double* dev = values;
     if (!is_device_ptr(values)) {
+        ensure_registered(s, values, s->vals_native.n * sizeof(double));
         CUDA_TRY(cudaMemcpyAsync(s->vals_native.p, values, s->vals_native.n * sizeof(double), cudaMemcpyHostToDevice,
                                  s->stream));
         dev = s->vals_native.p;
     }
+    s->last_values = dev;
     TRY(relayout(s, dev));
     TRY(prec_update(s));
     CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
@@ -1411,7 +1455,8 @@ int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, doubl
                                          : (nnzb - N) * blk + 16 * b * b * N + 40 * b * N + 16 * (N + 1) + 8 * N;
             break;
         case 2:
-            TRY(relayout(s, s->vals_native.p));
+            // (re-runs the last update from its device-resident values: a caller's device buffer must still be alive)
+            TRY(relayout(s, s->last_values ? s->last_values : s->vals_native.p));
             TRY(prec_update(s));
             bytes = 2 * nnzb * blk + 16 * b * b * N;
             break;

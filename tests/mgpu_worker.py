@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--prec", default="dilu")
     ap.add_argument("--b", type=int, default=3)
     ap.add_argument("--collectives", default="nccl", choices=["nccl", "p2p"])
-    ap.add_argument("--schedule", default="levels", choices=["levels", "tiles", "auto"])
+    ap.add_argument("--schedule", default="auto", choices=["levels", "tiles", "auto"])
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

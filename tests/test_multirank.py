@@ -44,12 +44,13 @@ def test_two_rank_block_jacobi(prec, b, collectives):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("schedule", ["tiles", "levels"])
 @pytest.mark.parametrize("prec", ["dilu", "ilu0"])
-def test_two_rank_block_jacobi_chunk_schedule(prec):
-    """the chunked-wavefront sweeps on local systems with ghost rows (4th upper entry of the first plane,
-    ghost rows ParallelOverlappingILU0 leaves alone)"""
+def test_two_rank_block_jacobi_both_schedules(prec, schedule):
+    """the tile walkers (the default on box grids) and the level schedule on local systems with ghost rows (4th upper
+    entry of the first plane, ghost rows ParallelOverlappingILU0 leaves alone)"""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
-    r = launch(2, ["--mode", "gpu", "--prec", prec, "--b", "3", "--collectives", "p2p", "--schedule", "tiles"],
-               29660 + (1 if prec == "ilu0" else 0))
+    r = launch(2, ["--mode", "gpu", "--prec", prec, "--b", "3", "--collectives", "p2p", "--schedule", schedule],
+               29660 + (1 if prec == "ilu0" else 0) + (2 if schedule == "levels" else 0))
     assert r.returncode == 0 and "MGPU_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
