@@ -17,6 +17,7 @@
 
 #include "../opmb200.h"
 
+#include <algorithm>
 #include <cstdint>
 #include <memory>
 #include <sstream>
@@ -86,9 +87,17 @@ public:
         check(opmb200_create(jsonOptions.empty() ? nullptr : jsonOptions.c_str(), blocksize,
                              static_cast<std::int64_t>(A.N()), static_cast<std::int64_t>(colidx.size()), rowptr.data(),
                              colidx.data(), static_cast<std::int64_t>(interiorSize), comm, halo, &h_));
-        update();
+        parallel_ = comm != nullptr;
+        try {
+            update(); // may throw Dune::MatrixBlockError (singular pivot block): a recoverable error in Flow
+        } catch (...) {
+            opmb200_destroy(h_); // no constructor has completed: ~Handle will not run
+            h_ = nullptr;
+            throw;
+        }
     }
     ~Handle() { opmb200_destroy(h_); }
+    bool parallel() const { return parallel_; }
     Handle(const Handle&) = delete;
     Handle& operator=(const Handle&) = delete;
 
@@ -102,6 +111,7 @@ public:
 private:
     const Matrix* A_;
     opmb200_solver* h_ = nullptr;
+    bool parallel_ = false;
 };
 
 #ifndef OPMB200_MATRIX_BLOCK_ERROR_T
@@ -116,6 +126,103 @@ void Handle<Matrix>::check(int status)
 {
     throwOnError<OPMB200_MATRIX_BLOCK_ERROR_T, OPMB200_SOLVER_ABORT_T>(status);
 }
+// status check for the helpers that have no matrix type at hand
+template <>
+class Handle<int>
+{
+public:
+    static void checkStatus(int status) { throwOnError<OPMB200_MATRIX_BLOCK_ERROR_T, OPMB200_SOLVER_ABORT_T>(status); }
+};
+
+// ---- parallel binding: Dune::OwnerOverlapCopyCommunication -> opmb200_halo + NCCL communicator ---------
+// What gpuistl/GpuAwareMPISender.hpp:164-222 derives from comm.remoteIndices(): per neighbour process the
+// owner rows this rank sends (entries of the process' send list whose LOCAL attribute is owner) and the copies
+// it receives (entries of the receive list whose REMOTE attribute is owner), both in the order of Dune's
+// remote index lists (ascending global index on both sides, so the two ends agree).
+struct FlatHalo {
+    std::size_t interiorSize = 0; // owner rows come first (ISTLSolver.hpp:299-306)
+    std::vector<int> neighbors, send_ptr, send_rows, recv_ptr, recv_rows;
+    opmb200_halo c {};            // views into the vectors above: valid while *this is alive and not moved from
+    void bind()
+    {
+        c.n_neighbors = static_cast<int>(neighbors.size());
+        c.neighbor_rank = neighbors.data();
+        c.send_ptr = send_ptr.data();
+        c.send_rows = send_rows.data();
+        c.recv_ptr = recv_ptr.data();
+        c.recv_rows = recv_rows.data();
+    }
+};
+
+template <class Comm>
+inline FlatHalo flattenHalo(const Comm& comm)
+{
+    constexpr int owner = 1; // Dune::OwnerOverlapCopyAttributeSet::owner
+    FlatHalo h;
+    std::size_t nOwner = 0, maxOwner = 0;
+    bool any = false;
+    for (const auto& index : comm.indexSet())
+        if (index.local().attribute() == owner) {
+            ++nOwner;
+            maxOwner = std::max<std::size_t>(maxOwner, index.local().local());
+            any = true;
+        }
+    if (any && maxOwner + 1 != nOwner)
+        throw std::invalid_argument("opmb200: owner rows must be numbered first (ghost-last ordering, ISTLSolver.hpp:299-306)");
+    h.interiorSize = nOwner;
+    h.send_ptr.push_back(0);
+    h.recv_ptr.push_back(0);
+    for (const auto& process : comm.remoteIndices()) {
+        std::vector<int> snd, rcv;
+        for (const auto& remote : *process.second.first)
+            if (remote.localIndexPair().local().attribute() == owner)
+                snd.push_back(static_cast<int>(remote.localIndexPair().local().local()));
+        for (const auto& remote : *process.second.second)
+            if (remote.attribute() == owner)
+                rcv.push_back(static_cast<int>(remote.localIndexPair().local().local()));
+        if (snd.empty() && rcv.empty())
+            continue;
+        h.neighbors.push_back(process.first);
+        h.send_rows.insert(h.send_rows.end(), snd.begin(), snd.end());
+        h.recv_rows.insert(h.recv_rows.end(), rcv.begin(), rcv.end());
+        h.send_ptr.push_back(static_cast<int>(h.send_rows.size()));
+        h.recv_ptr.push_back(static_cast<int>(h.recv_rows.size()));
+    }
+    h.bind();
+    return h;
+}
+
+// NCCL communicator of `size` ranks: the unique id is made on rank 0 and handed to the others by
+// `bcast128(void* buf)` (128 bytes, root 0) -- MPI_Bcast over comm.communicator() in Flow (ncclFromMpi below),
+// anything else in a test.  Device binding follows gpuistl/set_device.cpp: rank % number of devices.
+template <class Bcast>
+inline std::shared_ptr<opmb200_comm> makeComm(int rank, int size, Bcast&& bcast128)
+{
+    int ndev = 0;
+    Handle<int>::checkStatus(opmb200_device_count(&ndev));
+    if (ndev > 0)
+        Handle<int>::checkStatus(opmb200_set_device(rank % ndev));
+    unsigned char id[128] = {0};
+    if (rank == 0)
+        Handle<int>::checkStatus(opmb200_comm_unique_id(id));
+    bcast128(static_cast<void*>(id));
+    opmb200_comm* c = nullptr;
+    Handle<int>::checkStatus(opmb200_comm_create(rank, size, id, &c));
+    return std::shared_ptr<opmb200_comm>(c, [](opmb200_comm* p) { opmb200_comm_destroy(p); });
+}
+
+#if defined(HAVE_MPI) && HAVE_MPI
+// the one MPI-aware helper: Dune's communicator -> NCCL communicator over the same ranks
+template <class Comm>
+inline std::shared_ptr<opmb200_comm> ncclFromMpi(const Comm& comm)
+{
+    MPI_Comm mpi = comm.communicator();
+    int rank = 0, size = 1;
+    MPI_Comm_rank(mpi, &rank);
+    MPI_Comm_size(mpi, &size);
+    return makeComm(rank, size, [mpi](void* buf) { MPI_Bcast(buf, 128, MPI_BYTE, 0, mpi); });
+}
+#endif
 
 // Dune::PreconditionerWithUpdate<X,Y> (PreconditionerWithUpdate.hpp:32-41)
 template <class Operator>
@@ -139,7 +246,12 @@ public:
     }
     void update() override { h_->update(); }
     bool hasPerfectUpdate() const override { return true; } // DILU.hpp:165, ParallelOverlappingILU0.hpp:147-149
-    Dune::SolverCategory::Category category() const override { return Dune::SolverCategory::sequential; }
+    // with a communicator this IS the BlockPreconditioner-wrapped preconditioner (ghost restriction and
+    // copyOwnerToAll happen inside opmb200_precond_apply): overlapping, like OwningBlockPreconditioner.hpp:81-84
+    Dune::SolverCategory::Category category() const override
+    {
+        return h_->parallel() ? Dune::SolverCategory::overlapping : Dune::SolverCategory::sequential;
+    }
 
 private:
     std::shared_ptr<Handle<Matrix>> h_;
@@ -165,6 +277,16 @@ public:
         , prec_(std::make_shared<Preconditioner<Operator>>(h_))
     {
     }
+    // parallel, from Dune's communication object: FlexibleSolver(op, comm, prm, ...) (FlexibleSolver_impl.hpp:76-92).
+    // `nccl` comes from ncclFromMpi(comm) (or makeComm in a test) and is shared by all solvers of the rank.
+    template <class Comm>
+    Solver(const Operator& op, const Comm& comm, std::shared_ptr<opmb200_comm> nccl, const std::string& jsonOptions)
+        : nccl_(std::move(nccl))
+    {
+        FlatHalo halo = flattenHalo(comm);
+        h_ = std::make_shared<Handle<Matrix>>(op.getmat(), jsonOptions, halo.interiorSize, nccl_.get(), &halo.c);
+        prec_ = std::make_shared<Preconditioner<Operator>>(h_);
+    }
 
     void apply(X& x, X& b, Dune::InverseOperatorResult& res) override { apply(x, b, -1.0, res); }
 
@@ -180,12 +302,16 @@ public:
         Handle<Matrix>::check(status);
     }
 
-    Dune::SolverCategory::Category category() const override { return Dune::SolverCategory::sequential; }
+    Dune::SolverCategory::Category category() const override
+    {
+        return h_->parallel() ? Dune::SolverCategory::overlapping : Dune::SolverCategory::sequential;
+    }
     // FlexibleSolver::preconditioner(): ISTLSolver calls .update() on it every Newton step
     Dune::PreconditionerWithUpdate<X, X>& preconditioner() { return *prec_; }
     std::shared_ptr<Handle<Matrix>> handle() const { return h_; }
 
 private:
+    std::shared_ptr<opmb200_comm> nccl_; // keeps the communicator alive as long as the handle
     std::shared_ptr<Handle<Matrix>> h_;
     std::shared_ptr<Preconditioner<Operator>> prec_;
 };
@@ -200,9 +326,36 @@ inline void registerCreators()
     auto make = [](const char* type) {
         return [type](const Operator& op, const auto& prm, const auto& /*weights*/, std::size_t /*pressureIndex*/) {
             std::ostringstream js;
+            js.precision(17); // the relaxation factor must survive the round trip through JSON
             js << "{\"preconditioner\": {\"type\": \"" << type << "\", \"relaxation\": \""
                << prm.template get<double>("relaxation", 1.0) << "\"}}";
             auto h = std::make_shared<Handle<Matrix>>(op.getmat(), js.str());
+            return std::shared_ptr<Dune::PreconditionerWithUpdate<typename Operator::domain_type,
+                                                                  typename Operator::range_type>>(
+                std::make_shared<Preconditioner<Operator>>(h));
+        };
+    };
+    Factory::addCreator("b200dilu", make("dilu"));
+    Factory::addCreator("b200ilu0", make("ilu0"));
+}
+
+// The parallel creators (PreconditionerFactory.hpp:74-77 ParCreator: op, prm, weights, pressureIndex, comm).  The
+// preconditioner they return already contains what the reference gets from wrapping a serial preconditioner in
+// Dune::BlockPreconditioner (OwningBlockPreconditioner.hpp:31-92): ghost rows restricted, copyOwnerToAll after the
+// apply; category() is overlapping.  `nccl` is the rank's communicator (ncclFromMpi(comm)).
+template <class Factory, class Operator, class Comm>
+inline void registerParallelCreators(std::shared_ptr<opmb200_comm> nccl)
+{
+    using Matrix = typename Operator::matrix_type;
+    auto make = [nccl](const char* type) {
+        return [type, nccl](const Operator& op, const auto& prm, const auto& /*weights*/, std::size_t /*pressureIndex*/,
+                            const Comm& comm) {
+            std::ostringstream js;
+            js.precision(17);
+            js << "{\"preconditioner\": {\"type\": \"" << type << "\", \"relaxation\": \""
+               << prm.template get<double>("relaxation", 1.0) << "\"}}";
+            FlatHalo halo = flattenHalo(comm);
+            auto h = std::make_shared<Handle<Matrix>>(op.getmat(), js.str(), halo.interiorSize, nccl.get(), &halo.c);
             return std::shared_ptr<Dune::PreconditionerWithUpdate<typename Operator::domain_type,
                                                                   typename Operator::range_type>>(
                 std::make_shared<Preconditioner<Operator>>(h));

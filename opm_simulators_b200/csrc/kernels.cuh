@@ -425,7 +425,14 @@ constexpr int kMaxNeighbors = 16;
 struct P2PDev {
     int rank, size;
     double* mbox[kMaxRanks]; // rank p's mailboxes: records [2 parities][size senders][4 doubles]
+    // Sequence number of the reductions and epoch of the halo exchanges live in device memory and are advanced by
+    // the kernels themselves (the same on every rank: every rank runs the same kernel sequence), so that no kernel
+    // argument changes from launch to launch and the multi-rank iteration can be replayed as a CUDA graph.
+    unsigned long long* seq;
+    int* halo_epoch;
+    int* abort; // set when a peer did not answer within kSpinTimeoutCycles: the solve reports it instead of hanging
 };
+constexpr long long kSpinTimeoutCycles = 40000000000ll; // ~20 s at 1.965 GHz
 
 struct ReduceCtx {
     double* partials;      // [ND][max grid]
@@ -434,7 +441,6 @@ struct ReduceCtx {
     double* sums;          // multi-rank over NCCL: the local sums land here, ncclAllReduce and
     int defer;             //   epilogue_kernel follow on the stream (defer != 0)
     const P2PDev* p2p;     // multi-rank over peer memory: the all-reduce happens inside this kernel
-    unsigned long long seq; //   sequence number of this reduction (same on every rank)
 };
 
 __device__ __forceinline__ void st_sys(double* p, double v)
@@ -475,9 +481,13 @@ __device__ __forceinline__ int ld_sys(const int* p)
 // Mailboxes are double-buffered on the parity of the sequence number: a rank can be at most one
 // reduction ahead of the slowest rank, because it needs everybody's partial to finish one.
 template <int ND>
-__device__ __forceinline__ void p2p_allreduce(const P2PDev& c, unsigned long long seq, double (&acc)[ND])
+__device__ __forceinline__ void p2p_allreduce(const P2PDev& c, double (&acc)[ND])
 {
     const int lane = threadIdx.x & 31;
+    unsigned long long seq = 0;
+    if (lane == 0)
+        seq = ++(*c.seq); // this CTA is the only one of the rank that reduces
+    seq = __shfl_sync(0xffffffffu, seq, 0);
     const int par = (int)(seq & 1ull);
     double v[ND];
 #pragma unroll
@@ -491,7 +501,14 @@ __device__ __forceinline__ void p2p_allreduce(const P2PDev& c, unsigned long lon
         __threadfence_system();
         st_sys(reinterpret_cast<unsigned long long*>(dst + 3), seq);
         const double* src = c.mbox[c.rank] + (size_t)(par * c.size + lane) * 4;
-        while (ld_sys(reinterpret_cast<const unsigned long long*>(src + 3)) != seq) {}
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        while (ld_sys(reinterpret_cast<const unsigned long long*>(src + 3)) != seq) {
+            if ((++spins & 1023u) == 0 && clock64() - t0 > kSpinTimeoutCycles) { // a dead peer must not hang the others
+                st_relaxed(c.abort, 1);
+                break;
+            }
+        }
         __threadfence_system();
 #pragma unroll
         for (int d = 0; d < ND; ++d)
@@ -631,7 +648,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[ND], const ReduceCtx& rc
     __syncthreads();
     cta_sum<ND>(acc, red_smem);
     if (rc.p2p && threadIdx.x < 32)
-        p2p_allreduce<ND>(*rc.p2p, rc.seq, acc);
+        p2p_allreduce<ND>(*rc.p2p, acc);
     if (threadIdx.x == 0) {
         *rc.counter = 0u;
         if (rc.defer) {
@@ -1555,7 +1572,8 @@ __global__ void scatter_rows_kernel(int64_t n, int cnt, const int* __restrict__ 
 // ---- halo exchange over peer memory: copyOwnerToAll without NCCL --------------------------------------
 struct HaloDev {
     int nn;                          // neighbours
-    int epoch;                       // exchange number (host counter, same on every rank)
+    const int* epoch_ptr;            // exchanges completed so far (device counter, same on every rank)
+    int* abort;                      // see P2PDev
     int send_ptr[kMaxNeighbors + 1]; // rows sent to neighbour k: send_rows[send_ptr[k] .. send_ptr[k+1])
     int recv_ptr[kMaxNeighbors + 1];
     double* peer_recv[kMaxNeighbors]; // where neighbour k expects my rows (in ITS arena)
@@ -1572,8 +1590,16 @@ __global__ void __launch_bounds__(256) halo_push_kernel(HaloDev h, int64_t n, co
                                                         const double* __restrict__ v, unsigned int* counter)
 {
     // flow control: the neighbour must have consumed the previous exchange before we overwrite it
-    if ((int)threadIdx.x < h.nn)
-        while (ld_sys(h.my_ack + threadIdx.x) < h.epoch - 1) {}
+    const int epoch = *h.epoch_ptr + 1;
+    if ((int)threadIdx.x < h.nn) {
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        while (ld_sys(h.my_ack + threadIdx.x) < epoch - 1)
+            if ((++spins & 1023u) == 0 && clock64() - t0 > kSpinTimeoutCycles) {
+                st_relaxed(h.abort, 1);
+                break;
+            }
+    }
     __syncthreads();
     const int total = h.send_ptr[h.nn] * B;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
@@ -1591,7 +1617,7 @@ __global__ void __launch_bounds__(256) halo_push_kernel(HaloDev h, int64_t n, co
             *counter = 0u;
             __threadfence_system();
             for (int k = 0; k < h.nn; ++k)
-                st_sys(h.peer_dflag[k], h.epoch);
+                st_sys(h.peer_dflag[k], epoch);
         }
     }
 }
@@ -1599,10 +1625,18 @@ __global__ void __launch_bounds__(256) halo_push_kernel(HaloDev h, int64_t n, co
 // wait for every neighbour's rows, scatter them into the ghost rows, acknowledge
 template <int B>
 __global__ void __launch_bounds__(256) halo_pull_kernel(HaloDev h, int64_t n, const int* __restrict__ recv_rows, double* __restrict__ v,
-                                                        unsigned int* counter)
+                                                        unsigned int* counter, int* epoch_rw)
 {
-    if ((int)threadIdx.x < h.nn)
-        while (ld_sys(h.my_dflag + threadIdx.x) != h.epoch) {}
+    const int epoch = *h.epoch_ptr + 1;
+    if ((int)threadIdx.x < h.nn) {
+        const long long t0 = clock64();
+        unsigned spins = 0;
+        while (ld_sys(h.my_dflag + threadIdx.x) != epoch)
+            if ((++spins & 1023u) == 0 && clock64() - t0 > kSpinTimeoutCycles) {
+                st_relaxed(h.abort, 1);
+                break;
+            }
+    }
     __threadfence_system();
     __syncthreads();
     const int total = h.recv_ptr[h.nn] * B;
@@ -1617,7 +1651,8 @@ __global__ void __launch_bounds__(256) halo_pull_kernel(HaloDev h, int64_t n, co
         if (done == gridDim.x - 1) {
             *counter = 0u;
             for (int k = 0; k < h.nn; ++k)
-                st_sys(h.peer_ack[k], h.epoch);
+                st_sys(h.peer_ack[k], epoch);
+            *epoch_rw = epoch; // the exchange is complete on this rank (every CTA has read the old value long ago)
         }
     }
 }

@@ -160,8 +160,7 @@ struct opmb200_solver {
     DevBuf<P2PDev> p2p_dev;
     HaloDev halo_dev {};
     std::vector<void*> peer_base; // IPC mappings to close
-    unsigned long long seq = 0;   // reduction sequence number
-    int halo_epoch = 0;
+    DevBuf<unsigned long long> p2p_state; // [0] reduction sequence number, [1] halo epoch (int), [2] abort flag (int): device-resident
 
     // one BiCGSTAB iteration captured as a CUDA graph (single rank: every kernel argument is fixed
     // per solver, the scalars live on the device): the launch-bound chain of 9 kernels per iteration
@@ -209,12 +208,11 @@ struct opmb200_solver {
     }
 
     int64_t len() const { return L.n * b; }
-    // one call per reduction kernel launch: in p2p mode every call consumes a sequence number
     ReduceCtx rctx()
     {
         if (p2p)
-            return ReduceCtx {partials.p, counters.p, max_grid, sums.p, 0, p2p_dev.p, ++seq};
-        return ReduceCtx {partials.p, counters.p, max_grid, sums.p, n_ranks > 1 ? 1 : 0, nullptr, 0ull};
+            return ReduceCtx {partials.p, counters.p, max_grid, sums.p, 0, p2p_dev.p};
+        return ReduceCtx {partials.p, counters.p, max_grid, sums.p, n_ranks > 1 ? 1 : 0, nullptr};
     }
     Ticket ticket() { return Ticket {counters.p + 1, counters.p + 2}; }
     int slice_grid() const { return std::max(1, (L.n_slices + kWarpsPerCta - 1) / kWarpsPerCta); }
@@ -260,13 +258,13 @@ int copy_owner_to_all(opmb200_solver* s, double* v)
     const int ns = s->send_ptr.back(), nr = s->recv_ptr.back();
     if (s->p2p) {
         // peer memory: push my owner rows into the neighbours' receive buffers, then pull theirs
-        HaloDev h = s->halo_dev;
-        h.epoch = ++s->halo_epoch;
+        const HaloDev& h = s->halo_dev;
         const int gpush = std::max(1, std::min(64, (ns * b + 255) / 256));
         const int gpull = std::max(1, std::min(64, (nr * b + 255) / 256));
         DISPATCH_B(b, (halo_push_kernel<B><<<gpush, 256, 0, s->stream>>>(h, s->L.n, s->send_rows.p, v, s->counters.p + 3)));
         TRY(check_launch(s, "halo_push"));
-        DISPATCH_B(b, (halo_pull_kernel<B><<<gpull, 256, 0, s->stream>>>(h, s->L.n, s->recv_rows.p, v, s->counters.p + 3)));
+        DISPATCH_B(b, (halo_pull_kernel<B><<<gpull, 256, 0, s->stream>>>(h, s->L.n, s->recv_rows.p, v, s->counters.p + 3,
+                                                                        reinterpret_cast<int*>(s->p2p_state.p + 1))));
         return check_launch(s, "halo_pull");
     }
     if (ns > 0) {
@@ -759,7 +757,8 @@ int do_solve(opmb200_solver* s, double* x, double* b, double reduction, opmb200_
     while (true) {
         const bool can_enqueue = enq < s->maxiter;
         if (can_enqueue) {
-            if (s->use_graph && s->n_ranks == 1 && s->op_repeats <= 1 && !s->trace) {
+            // (multi-rank: only with the peer-memory collectives -- no NCCL call, no kernel argument that changes)
+            if (s->use_graph && (s->n_ranks == 1 || s->p2p) && s->op_repeats <= 1 && !s->trace) {
                 if (!s->iter_graph) {
                     cudaGraph_t g = nullptr;
                     const int64_t l0 = s->launches;
@@ -826,6 +825,12 @@ int do_solve(opmb200_solver* s, double* x, double* b, double reduction, opmb200_
         for (size_t i = 0; i < s->last_hist.size(); ++i)
             std::printf("%5.1f %16.8e %16.8e\n", 0.5 * i, s->last_hist[i],
                         i ? s->last_hist[i] / s->last_hist[i - 1] : 0.0);
+    }
+    if (s->p2p) { // a peer that stopped answering: the kernels gave up after ~20 s instead of hanging
+        int aborted = 0;
+        CUDA_TRY(cudaMemcpy(&aborted, s->p2p_state.p + 2, sizeof(int), cudaMemcpyDeviceToHost));
+        if (aborted)
+            return fail(OPMB200_NCCL_ERROR, "a peer rank did not answer within the spin time-out (peer-memory collectives)");
     }
     if (fin.abort_code == 1)
         return fail(OPMB200_SOLVER_ABORT, "breakdown in BiCGSTAB (rho, omega or h <= EPSILON) after "
@@ -1156,6 +1161,29 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
         CUDA_TRY(s->recv_rows.upload(rp, st));
         CUDA_TRY(s->send_buf.alloc(sp.size() * block_size));
         CUDA_TRY(s->recv_buf.alloc(rp.size() * block_size));
+        {   // Every rank's send counts must equal the receiver's receive counts (one all-gather at create time): a
+            // mis-flattened halo would otherwise write beyond a peer's receive region or hang an NCCL Send/Recv pair.
+            const int P = s->n_ranks, me = comm->rank;
+            std::vector<int> mine(P, 0), all((size_t)P * P, 0), want(P, 0);
+            for (int k = 0; k < nn; ++k) {
+                const int o = s->nb_rank[k];
+                if (o < 0 || o >= P || o == me)
+                    return fail(OPMB200_INVALID_ARGUMENT, "halo neighbour rank out of range");
+                mine[o] = s->send_ptr[k + 1] - s->send_ptr[k];
+                want[o] = s->recv_ptr[k + 1] - s->recv_ptr[k];
+            }
+            DevBuf<int> d_mine, d_all;
+            CUDA_TRY(d_mine.upload(mine, st));
+            CUDA_TRY(d_all.alloc(all.size()));
+            NCCL_TRY(ncclAllGather(d_mine.p, d_all.p, P, ncclInt, comm->comm, st));
+            CUDA_TRY(cudaMemcpyAsync(all.data(), d_all.p, all.size() * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            for (int o = 0; o < P; ++o)
+                if (o != me && all[(size_t)o * P + me] != want[o])
+                    return fail(OPMB200_INVALID_ARGUMENT, "halo mismatch: rank " + std::to_string(o) + " sends "
+                                                              + std::to_string(all[(size_t)o * P + me]) + " rows to rank "
+                                                              + std::to_string(me) + " which expects " + std::to_string(want[o]));
+        }
         if (nn > kMaxNeighbors || s->n_ranks > kMaxRanks)
             return fail(OPMB200_INVALID_ARGUMENT, "too many ranks / neighbours for the peer-to-peer tables");
         // peer-to-peer arena (used once opmb200_p2p_import has mapped the peers)
@@ -1503,6 +1531,7 @@ struct P2PBlob {
     int peer[kMaxNeighbors];
     long long recv_off[kMaxNeighbors], dflag_off[kMaxNeighbors], ack_off[kMaxNeighbors];
     long long mbox_off;
+    int recv_cnt[kMaxNeighbors]; // rows this rank expects from peer k: the sender checks its own count against it
 };
 static_assert(sizeof(P2PBlob) <= OPMB200_P2P_BLOB_BYTES, "blob too large");
 } // namespace
@@ -1523,6 +1552,7 @@ int opmb200_p2p_export(opmb200_solver* s, void* blob)
         b.recv_off[k] = (long long)(s->off_recv + (size_t)s->recv_ptr[k] * s->b * sizeof(double));
         b.dflag_off[k] = (long long)(s->off_dflag + (size_t)k * sizeof(int));
         b.ack_off[k] = (long long)(s->off_ack + (size_t)k * sizeof(int));
+        b.recv_cnt[k] = s->recv_ptr[k + 1] - s->recv_ptr[k];
     }
     b.mbox_off = (long long)s->off_mbox;
     std::memset(blob, 0, OPMB200_P2P_BLOB_BYTES);
@@ -1560,6 +1590,11 @@ int opmb200_p2p_import(opmb200_solver* s, const void* blobs)
     dev.size = P;
     for (int p = 0; p < P; ++p)
         dev.mbox[p] = reinterpret_cast<double*>(base[p] + all[p].mbox_off);
+    CUDA_TRY(s->p2p_state.alloc(4));
+    CUDA_TRY(cudaMemset(s->p2p_state.p, 0, 4 * sizeof(unsigned long long)));
+    dev.seq = s->p2p_state.p;
+    dev.halo_epoch = reinterpret_cast<int*>(s->p2p_state.p + 1);
+    dev.abort = reinterpret_cast<int*>(s->p2p_state.p + 2);
     CUDA_TRY(s->p2p_dev.alloc(1));
     CUDA_TRY(cudaMemcpy(s->p2p_dev.p, &dev, sizeof dev, cudaMemcpyHostToDevice));
     HaloDev& h = s->halo_dev;
@@ -1577,10 +1612,17 @@ int opmb200_p2p_import(opmb200_solver* s, const void* blobs)
                 j = i;
         if (j < 0)
             return fail(OPMB200_INVALID_ARGUMENT, "halo is not symmetric: rank " + std::to_string(o) + " does not list me");
+        // the push kernel writes send_ptr[k+1]-send_ptr[k] rows straight into the peer's receive region
+        if (s->send_ptr[k + 1] - s->send_ptr[k] != all[o].recv_cnt[j])
+            return fail(OPMB200_INVALID_ARGUMENT, "halo mismatch: I send " + std::to_string(s->send_ptr[k + 1] - s->send_ptr[k])
+                                                      + " rows to rank " + std::to_string(o) + " which expects "
+                                                      + std::to_string(all[o].recv_cnt[j]));
         h.peer_recv[k] = reinterpret_cast<double*>(base[o] + all[o].recv_off[j]);
         h.peer_dflag[k] = reinterpret_cast<int*>(base[o] + all[o].dflag_off[j]);
         h.peer_ack[k] = reinterpret_cast<int*>(base[o] + all[o].ack_off[j]);
     }
+    h.epoch_ptr = dev.halo_epoch;
+    h.abort = dev.abort;
     h.my_recv = reinterpret_cast<const double*>(s->arena.p + s->off_recv);
     h.my_dflag = reinterpret_cast<int*>(s->arena.p + s->off_dflag);
     h.my_ack = reinterpret_cast<int*>(s->arena.p + s->off_ack);

@@ -2,6 +2,7 @@
 // include/opmb200/dune_adapter.hpp binds to (dune-istl is not installed in this image).  Same
 // class and member names as the originals; only what the adapter touches is implemented.
 #pragma once
+#include <algorithm>
 #include <cstddef>
 #include <functional>
 #include <map>
@@ -138,6 +139,77 @@ public:
     SolverCategory::Category category() const { return SolverCategory::sequential; }
 private:
     const M& A_;
+};
+
+// ---- Dune::OwnerOverlapCopyCommunication<G,L>: only what the halo flattening reads -------------------------
+// (dune-istl owneroverlapcopy.hh, dune-common parallel/{indexset,remoteindices,plocalindex}.hh)
+struct OwnerOverlapCopyAttributeSet { enum AttributeSet { owner = 1, overlap = 2, copy = 3 }; };
+
+struct ParallelLocalIndexStub {
+    std::size_t local_;
+    int attribute_;
+    std::size_t local() const { return local_; }
+    int attribute() const { return attribute_; }
+};
+struct IndexPairStub {
+    int global_;
+    ParallelLocalIndexStub local_;
+    int global() const { return global_; }
+    const ParallelLocalIndexStub& local() const { return local_; }
+};
+struct RemoteIndexStub {
+    int attribute_;          // the attribute of the index on the REMOTE process
+    const IndexPairStub* pair_;
+    int attribute() const { return attribute_; }
+    const IndexPairStub& localIndexPair() const { return *pair_; }
+};
+using RemoteIndexListStub = std::vector<RemoteIndexStub>;
+
+template <class G, class L>
+class OwnerOverlapCopyCommunication
+{
+public:
+    using ParallelIndexSet = std::vector<IndexPairStub>; // sorted by global index, like Dune's
+    // rank -> (send list, receive list), as Dune::RemoteIndices: both sorted by global index
+    using RemoteIndices = std::map<int, std::pair<RemoteIndexListStub*, RemoteIndexListStub*>>;
+
+    // `globalOf[l]`, `attr[l]` per local index; `ownerRank[l]` the rank that owns it; `peerHas[p]` the global
+    // indices present on rank p (what the two sides of Dune's RemoteIndices::rebuild exchange)
+    OwnerOverlapCopyCommunication(int rank, const std::vector<int>& globalOf, const std::vector<int>& attr,
+                                  const std::map<int, std::vector<std::pair<int, int>>>& peerIndices /* rank -> (global, attr there) */)
+        : rank_(rank)
+    {
+        std::vector<std::size_t> order(globalOf.size());
+        for (std::size_t l = 0; l < order.size(); ++l)
+            order[l] = l;
+        std::sort(order.begin(), order.end(), [&](std::size_t a, std::size_t b) { return globalOf[a] < globalOf[b]; });
+        for (std::size_t l : order)
+            index_.push_back(IndexPairStub {globalOf[l], ParallelLocalIndexStub {l, attr[l]}});
+        std::map<int, const IndexPairStub*> byGlobal;
+        for (const auto& ip : index_)
+            byGlobal[ip.global()] = &ip;
+        for (const auto& peer : peerIndices) {
+            auto& lists = store_[peer.first];
+            for (const auto& ga : peer.second) { // ascending global index
+                auto it = byGlobal.find(ga.first);
+                if (it == byGlobal.end())
+                    continue; // not shared with that rank
+                lists.first.push_back(RemoteIndexStub {ga.second, it->second});
+                lists.second.push_back(RemoteIndexStub {ga.second, it->second});
+            }
+            if (!lists.first.empty())
+                remote_[peer.first] = {&lists.first, &lists.second};
+        }
+    }
+    const ParallelIndexSet& indexSet() const { return index_; }
+    const RemoteIndices& remoteIndices() const { return remote_; }
+    int rank() const { return rank_; }
+
+private:
+    int rank_;
+    ParallelIndexSet index_;
+    std::map<int, std::pair<RemoteIndexListStub, RemoteIndexListStub>> store_;
+    RemoteIndices remote_;
 };
 
 } // namespace Dune
