@@ -12,7 +12,7 @@ variants = [int(v) for v in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0
 for prec in (sys.argv[5].split(",") if len(sys.argv) > 5 else ("dilu", "ilu0")):
     for thr in variants:
         t=time.time()
-        fs = FlexibleSolver(MatrixAdapter(A), {"tol": 1e-2, "maxiter": 200, "preconditioner": {"type": prec}, "b200": ({"throttle_levels": thr} if sched == "levels" else {"schedule": sched, "chunk_rows": thr})})
+        fs = FlexibleSolver(MatrixAdapter(A), {"tol": 1e-2, "maxiter": 200, "preconditioner": {"type": prec}, "b200": ({"schedule": "levels", "throttle_levels": thr} if sched == "levels" else {"schedule": sched, "chunk_rows": thr, "ctas_per_sm": int(os.environ.get("CPS", "1")), "poll_warps": int(os.environ.get("POLL", "4"))})})
         info = fs.info(); 
         print(prec, sched, "variant", thr, "schedule built", info["schedule"], "create+update %.2fs" % (time.time()-t), "analysis %.2fs" % info["t_analysis_s"], "update_ms %.3f" % info["t_update_ms"], "levels", info["n_levels"], "slices", info["n_slices"], "padded", info["padded_blocks"]/info["nnzb"], "chunks", info["n_chunks"], "chunk_rows", info["chunk_rows"], "est_steps", info["est_steps"], flush=True)
         for what, name in ((0,"spmv"),(1,"prec_apply"),(4,"lower"),(5,"upper"),(2,"prec_update"),(3,"vec3")):

@@ -2,7 +2,7 @@
 
   python scripts/replay_system.py --matrix J.mm --rhs r.mm [--block 3]          # Dune storeMatrixMarket dumps
   python scripts/replay_system.py --export-dir export/ --block 3                 # exportSystem.hpp raw binaries
-  ... [--options opts.json | --prec dilu|ilu0 --tol 1e-2 --maxiter 200] [--schedule levels|chunks] [--check] [--reps 3]
+  ... [--options opts.json | --prec dilu|ilu0 --tol 1e-2 --maxiter 200] [--schedule auto|levels|tiles] [--check] [--reps 3]
 
 --check solves the same system with the CPU oracle (the restated Dune path) and reports the differences."""
 import argparse, json, os, sys, time
@@ -15,7 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--matrix"); ap.add_argument("--rhs"); ap.add_argument("--export-dir")
 ap.add_argument("--block", type=int, default=None)
 ap.add_argument("--options"); ap.add_argument("--prec", default="dilu"); ap.add_argument("--tol", type=float, default=1e-2)
-ap.add_argument("--maxiter", type=int, default=200); ap.add_argument("--schedule", default="levels")
+ap.add_argument("--maxiter", type=int, default=200); ap.add_argument("--schedule", default="auto")
 ap.add_argument("--check", action="store_true"); ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 if a.export_dir:
@@ -45,6 +45,9 @@ if a.check:
     xo, ro, _ = orc.solve_serial(A.rowptr, A.col, A.val, rhs, prec=str(po.get("type", "ilu0")).lower().replace("paroverilu0", "ilu0"),
                                  tol=float(opts.get("tol", 1e-2)), maxiter=int(opts.get("maxiter", 200)),
                                  relaxation=float(po.get("relaxation", 1.0)))
-    print(f"oracle: iterations {ro['iterations']} reduction {ro['reduction']:.3e}; |x - x_oracle| / |x_oracle| = "
-          f"{np.linalg.norm(x - xo) / max(np.linalg.norm(xo), 1e-300):.3e}")
+    err = np.linalg.norm(x - xo) / max(np.linalg.norm(xo), 1e-300)
+    print(f"oracle: iterations {ro['iterations']} reduction {ro['reduction']:.3e}; |x - x_oracle| / |x_oracle| = {err:.3e}")
+    print(json.dumps({"replay_check": {"n": A.n, "b": A.b, "iterations": res.iterations, "oracle_iterations": ro["iterations"],
+                                       "x_rel_err": float(err), "padded_blocks_ratio": info["padded_blocks"] / info["nnzb"],
+                                       "schedule": info["schedule"]}}))
 fs.close()

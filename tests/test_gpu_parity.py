@@ -405,3 +405,35 @@ def test_tile_chunks_equal_the_level_schedule_bit_for_bit(b, prec, schedule):
         # the solve differs in the last bits only (the dot products add the rows in schedule order)
         assert abs(out[name][2] - out["levels"][2]) <= 1
         assert rel_err(out[name][1], out["levels"][1]) < 1e-6
+
+
+# ---- on-disk systems: what a Flow build dumps, replayed through the library -------------
+@pytest.mark.parametrize("fmt", ["matrixmarket", "export"])
+def test_replayed_dump_matches_the_oracle(tmp_path, fmt, schedule):
+    """a Norne-sized irregular Jacobian (C2: inactive cells, NNCs) written the way ISTLSolver dumps systems at verbosity > 10
+    (Dune storeMatrixMarket, WriteSystemMatrixHelper.hpp:63-94) or exportSystem.hpp:40-139 writes them, read back by
+    scripts/replay_system.py and solved on the GPU: iterations and solution against the oracle"""
+    import json
+    import subprocess
+    import sys
+
+    from conftest import ROOT
+    from opm_simulators_b200 import matrixmarket
+
+    if schedule != "levels":
+        pytest.skip("one schedule is enough: the replay picks its own (auto)")
+    s = generators.config("C2", scale=0.5)
+    A = s["A"]
+    if fmt == "matrixmarket":
+        matrixmarket.write_matrix(str(tmp_path / "J.mm"), A)
+        matrixmarket.write_vector(str(tmp_path / "r.mm"), s["rhs2"], A.b)
+        args = ["--matrix", str(tmp_path / "J.mm"), "--rhs", str(tmp_path / "r.mm"), "--block", "3"]
+    else:
+        matrixmarket.export_system(str(tmp_path), A, s["rhs2"])
+        args = ["--export-dir", str(tmp_path), "--block", "3"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "replay_system.py"), *args, "--prec", "dilu", "--tol", "1e-2",
+                        "--check", "--reps", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    line = [l for l in r.stdout.splitlines() if l.startswith('{"replay_check"')][-1]
+    c = json.loads(line)["replay_check"]
+    assert c["n"] == A.n and c["iterations"] == c["oracle_iterations"] and c["x_rel_err"] < 1e-10
