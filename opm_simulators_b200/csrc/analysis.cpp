@@ -316,9 +316,10 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
     const int max_slots = b >= 3 ? 4 : 3; // instantiated tile walkers (solver.cu, DISPATCH_BS)
     if (schedule_mode != 0 && (max_wl > max_slots || max_wu > max_slots || n >= (int64_t)kTwExt))
         schedule_mode = 0;
-    // rows of one CTA step: the tile walkers take kTwWarps * (32 / b), but a step is also one slice of the SELL
-    // layout the SpMV and the factorisation kernels work on, so no more than a slice
-    const int R = std::min(kTwWarps * (32 / b), kSlice);
+    // rows of one CTA step of the tile walkers == one slice of the SELL layout the SpMV and the factorisation
+    // kernels work on
+    const int R = kTwRows;
+    static_assert(kTwRows == kSlice, "a step is a slice");
     int32_t nlev = 0;
     for (int64_t i = 0; i < n; ++i)
         nlev = std::max(nlev, lev[i] + 1);
@@ -470,7 +471,7 @@ int build_layout(int b, int64_t n, int64_t nnzb, const int32_t* rowptr, const in
     // before the first row of a step (behind its last row, upper sweep) is intact.
     int tw_window = 0;
     if (schedule_mode == 1) {
-        L.tw_rows = kTwWarps * (32 / b); // what the kernels' record layout provides for
+        L.tw_rows = R;
         L.tw_ring = 256;
         while (L.tw_ring < 4 * L.tw_rows)
             L.tw_ring *= 2;

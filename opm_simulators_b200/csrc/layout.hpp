@@ -27,6 +27,7 @@ constexpr int kSlice = 32;
 constexpr int32_t kTwRing = 1 << 30, kTwExt = 1 << 29; // dependency codes of the tile walkers
 constexpr int kTwMaxExt = 32;                        // external dependencies per step (one per poll lane)
 constexpr int kTwWarps = 4;                          // compute warps of a tile walker
+constexpr int kTwRows = 32;                          // rows of a step (one SELL slice): kTwWarps x 8 rows, b lanes each
 
 struct Layout {
     int b = 0;
@@ -69,7 +70,7 @@ struct Layout {
     std::vector<int32_t> slot_col; // [n_slot_rows*32]
     std::vector<int32_t> slot_src; // [n_slot_rows*32]
     // ---- mode 1: step tables of the tile walkers (tile_kernels.cuh) ------------------------------
-    int tw_rows = 0;                  // rows per CTA step: 4 warps x (32 / b) rows
+    int tw_rows = 0;                  // rows per CTA step: kTwRows
     int tw_ring = 0;                  // positions of a chunk's shared-memory ring (power of two)
     int tw_slots[2] = {3, 3};         // dependency slots per row: lower, upper (3 or 4)
     int n_steps = 0;

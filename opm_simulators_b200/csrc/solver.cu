@@ -406,7 +406,7 @@ int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
         c.prefetch = s->prefetch;
         c.debug = s->debug;
         c.poll_warps = s->poll_warps;
-        const int threads = (kTwWarps + 1 + s->poll_warps) * 32;
+        const int threads = (kTwWarps + 2 + s->poll_warps) * 32; // compute, loader, publisher, poll warps
         c.ticket = a.ticket;
         c.sc = a.sc;
         c.check_done = a.check_done;

@@ -29,16 +29,17 @@
 namespace opmb200 {
 
 constexpr int kTwMaxPollWarps = 6;
-// launch bound; the launch picks the poll warps.  ONE CTA per SM: two co-resident tile walkers slow each other
-// down by more than they gain (C3: 250 us with two per SM, 205 us with one -- measured)
-constexpr int kTwMaxThreads = (kTwWarps + 1 + kTwMaxPollWarps) * 32;
+// launch bound: compute warps, loader, publisher, poll warps; the launch picks the poll warps.  ONE CTA per SM: two
+// co-resident tile walkers slow each other down by more than they gain (C3: 250 us with two per SM, 205 us with one)
+constexpr int kTwMaxThreads = (kTwWarps + 2 + kTwMaxPollWarps) * 32;
 
 template <int B, int S, bool DINV, bool UPPER>
 struct TwCfg {
     static constexpr int NW = kTwWarps;               // compute warps
-    static constexpr int RPW = 32 / B;                // rows per warp
-    static constexpr int R = NW * RPW;                // rows per step
-    static constexpr int RP = (R + 3) & ~3;
+    static constexpr int RPW = kTwRows / NW;          // rows per warp: 8 (b lanes each; b = 3: 24 of a warp's 32 lanes work)
+    static constexpr int LW = RPW * B;                // working lanes per warp
+    static constexpr int R = kTwRows;                 // rows per step == one SELL slice
+    static constexpr int RP = R;
     static constexpr int W = Rec<B>::W;               // doubles per dependency record in global memory
     static constexpr int NV = S * B + (DINV ? B : 0); // doubles per lane and step
     static constexpr int NP = (NV + 1) / 2;           // ... as 16-byte pairs
@@ -49,17 +50,20 @@ struct TwCfg {
     static constexpr int kArmOff = 32;                               // 128 bits: rows somebody polls in the other sweep
     static constexpr int kExtPosOff = 48;                            // kTwMaxExt positions
     static constexpr int kCodeOff = kExtPosOff + kTwMaxExt * 4;      // [S][RP] dependency codes
-    static constexpr int kValOff = (kCodeOff + S * RP * 4 + 15) & ~15; // [NW][NP][32] double2
-    static constexpr int kRecBytes = kValOff + NW * NP * 512;
+    static constexpr int kValOff = (kCodeOff + S * RP * 4 + 15) & ~15; // [NW][NP][LW] double2: no bytes for idle lanes
+    static constexpr int kRecBytes = kValOff + NW * NP * LW * 16;
     // what the loader and the poll warps add to a stage.  Right-hand side: upper = the lower sweep's records
     // [RP][W]; lower = the step's runs of the component-major solver vector [B][RP]
     static constexpr int kRhsOff = kRecBytes;
     static constexpr int kRhsBytes = UPPER ? RP * W * 8 : B * RP * 8;
     static constexpr int kExtValOff = kRhsOff + kRhsBytes;           // [kTwMaxExt][4] doubles
     static constexpr int kStageBytes = (kExtValOff + kTwMaxExt * 32 + 127) & ~127;
-    // stages: what fits in ~128 KB
+    // stages: what fits in ~128 KB, and no more than the ring can back -- a stage is free once the publisher warp has
+    // stored its step from the ring, and a ring slot is overwritten RING / 32 steps later at the earliest (a step
+    // has at most 32 rows, csrc/analysis.cpp)
     static constexpr int kStagesRaw = 131072 / kStageBytes;
-    static constexpr int kStages = kStagesRaw < 2 ? 2 : (kStagesRaw > 8 ? 8 : kStagesRaw);
+    static constexpr int kStagesCap = RING / 32 < 8 ? RING / 32 : 8;
+    static constexpr int kStages = kStagesRaw < 2 ? 2 : (kStagesRaw > kStagesCap ? kStagesCap : kStagesRaw);
     static constexpr int kRingOff = kStages * kStageBytes;           // [RING][4] doubles
     static constexpr int kZeroOff = kRingOff + RING * 32;            // one all-zero record
     static constexpr int kBarOff = kZeroOff + 32;                    // kStages "data", then kStages "ext" mbarriers
@@ -67,7 +71,7 @@ struct TwCfg {
     static constexpr int kSmemBytes = kCtlOff + 32;
 };
 // control words in shared memory
-enum TwCtl { kCtlReleased = 0, kCtlRec0 = 1, kCtlSteps = 2, kCtlStop = 3, kCtlQ0 = 4, kCtlQ1 = 5 };
+enum TwCtl { kCtlReleased = 0, kCtlRec0 = 1, kCtlSteps = 2, kCtlStop = 3, kCtlQ0 = 4, kCtlQ1 = 5, kCtlPublished = 6 };
 
 struct TwArgs {
     int nchunks;
@@ -172,8 +176,6 @@ template <int B, int S, int NP>
 struct TwStep {
     int q0, count, flags;
     unsigned xaddr[S]; // where dependency s is found (ring, the stage's external slots, the zero record)
-    int pub;           // bit rho & 31: another chunk polls the row's result: it is published with a strong store
-    int arm;           // bit rho & 31: the row is polled in the other sweep: its record there is (re-)armed
 };
 
 // ---- compute warps -------------------------------------------------------------------------------
@@ -197,15 +199,11 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
     unsigned long long* data_bar = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
     unsigned long long* ext_bar = data_bar + NS;
     volatile int* ctl = reinterpret_cast<volatile int*>(smem + T::kCtlOff);
-    double* out = UPPER ? a.vpoll : a.tmp;
-    double* arm = UPPER ? a.tmp : a.vpoll;
-    const double sent = sentinel();
     const bool zero_ghosts = !UPPER && ILU0 && a.ghost_zero;
     // per-lane constants of the look-ahead
     const unsigned code_o = T::kCodeOff + (unsigned)rho * 4;
-    const unsigned val_o = T::kValOff + (unsigned)(warp * T::NP * 32 + lane) * 16;
+    const unsigned val_o = T::kValOff + (unsigned)(warp * T::NP * T::LW + (lane_ok ? lane : 0)) * 16;
     const unsigned in_o = T::kRhsOff + (unsigned)(UPPER ? rho * T::W + r : r * T::RP + rho) * 8;
-    const unsigned pub_o = T::kPubOff + (unsigned)(rho >> 5) * 4, arm_o = T::kArmOff + (unsigned)(rho >> 5) * 4;
     TWP_DECL;
 
     // everything about the step in stage `st` that does not depend on the steps before it: loads and
@@ -215,8 +213,6 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
         N.q0 = lds_s32(sb + T::kHdrOff);
         N.count = lds_s32(sb + T::kHdrOff + 4);
         N.flags = lds_s32(sb + T::kHdrOff + 12);
-        N.pub = lds_s32(sb + pub_o);
-        N.arm = lds_s32(sb + arm_o);
 #pragma unroll
         for (int s = 0; s < S; ++s) {
             // kTwRing + index: the chunk's ring (index RING = the zero record behind it: "no dependency");
@@ -241,15 +237,10 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
             st1 = 0;
             par1 ^= 1u;
         }
-        // ---- what may loop first ------------------------------------------------------------------
-        // (both tests issue back to back: a test of a completed phase takes ~90 cycles.  Never test a phase that
-        // will not complete -- the last step's "next stage": the test blocks until it times out)
-        const bool ok1 = t + 1 < ns ? mbar_try_wait(data_bar + st1, par1) : true; // the next step's record: landed long ago, normally
-        const bool ok0 = mbar_try_wait(ext_bar + st, par);    // this step's right-hand side and externals are parked
-        if (!ok0)
-            mbar_wait(ext_bar + st, par);
-        if (!ok1)
-            mbar_wait(data_bar + st1, par1);
+        // ---- what may loop first: ONE barrier ---------------------------------------------------------
+        // this step's right-hand side and externals are parked -- and the poll warp that says so has seen the NEXT
+        // step's record land (a second test of a completed phase here cost ~100 cycles per step)
+        mbar_wait(ext_bar + st, par);
         TWP_MARK(t < 8 ? 6 : 0);
         // ---- the step proper: one basic block ------------------------------------------------------
         double x[S][B];
@@ -270,7 +261,7 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
         double av[2 * T::NP];
 #pragma unroll
         for (int k = 0; k < T::NP; ++k)
-            lds_v2(sb0 + val_o + (unsigned)k * 512, av[2 * k], av[2 * k + 1]);
+            lds_v2(sb0 + val_o + (unsigned)k * T::LW * 16, av[2 * k], av[2 * k + 1]);
         double in = lds_f64(sb0 + in_o);
         in = (zero_ghosts && (C.flags & 1)) ? 0.0 : in; // ParallelOverlappingILU0 never touches ghost rows
         look_ahead(st1, N);
@@ -313,29 +304,8 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
         TWP_MARK(1);
         named_bar_sync(1, T::NW * 32); // the ring writes are visible to the four warps; everybody is done with the stage
         if (threadIdx.x == 0)
-            ctl[kCtlReleased] = g + 1; // the stage may be refilled
+            ctl[kCtlReleased] = g + 1; // the publisher warp stores the step's results from the ring and frees the stage
         TWP_MARK(2);
-        // Publish BEHIND the barrier, from the registers: a barrier waits for the L2's acknowledgement of the
-        // strong stores in front of it (+200 cycles per step, measured); here they travel while the next step
-        // waits for its externals.  Only rows another chunk polls get a strong store (and only those have a
-        // sentinel to arm): the rest of y is read by the upper sweep (a later kernel), the rest of the upper
-        // sweep's records by nobody.  (Deferring the weak stores into the next step's block was measured: no gain --
-        // a lone warp per scheduler is bound by its instruction count, ~5 cycles per instruction, not by the chain.)
-        if (active && !TW_DBG(1)) {
-            const bool polled = (C.pub >> (rho & 31)) & 1;
-            if (UPPER) {
-                if (polled)
-                    st_relaxed(out + (size_t)q * T::W + r, res);
-                a.v[VIDX(a.n, q, r)] = res;
-            } else {
-                if (polled)
-                    st_relaxed(out + (size_t)q * T::W + r, res);
-                else
-                    out[(size_t)q * T::W + r] = res;
-            }
-            if ((C.arm >> (rho & 31)) & 1)
-                arm[(size_t)q * T::W + r] = sent; // lower: arm the upper sweep's records; upper: re-arm for the next apply
-        }
         TWP_MARK(3);
         st = st1;
         par = par1;
@@ -384,7 +354,7 @@ __device__ __forceinline__ void tw_loader(const TwArgs& a, unsigned char* smem, 
         if (PF > 0 && (t & 3) == 0 && t + NS + PF < ns && !TW_DBG(16)) // four records per prefetch
             l2_prefetch_bulk(rec + (size_t)(NS + PF) * T::kRecBytes, (unsigned)(min(4, ns - t - NS - PF) * T::kRecBytes));
         TWP_MARK(0);
-        while (ctl[kCtlReleased] < g + 1 - NS) {} // plain spin (a __nanosleep would cost a microsecond)
+        while (ctl[kCtlPublished] < g + 1 - NS) {} // plain spin (a __nanosleep would cost a microsecond)
         TWP_MARK(1);
         const unsigned bytes = TW_DBG(4) ? 48u : (unsigned)T::kRecBytes; // timing experiment: header only
         mbar_expect_tx(data_bar + st, bytes);
@@ -401,7 +371,8 @@ __device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, 
     constexpr bool DINV = !(ILU0 && !UPPER);
     using T = TwCfg<B, S, DINV, UPPER>;
     constexpr int NS = T::kStages;
-    unsigned long long* ext_bar = reinterpret_cast<unsigned long long*>(smem + T::kBarOff) + NS;
+    unsigned long long* data_bar = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
+    unsigned long long* ext_bar = data_bar + NS;
     volatile int* ctl = reinterpret_cast<volatile int*>(smem + T::kCtlOff);
     const double* out = UPPER ? a.vpoll : a.tmp;
     const unsigned char* rec = a.stream + (size_t)(rec0 + pw) * T::kRecBytes;
@@ -475,7 +446,11 @@ __device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, 
         }
         __syncwarp();
         TWP_MARK(1);
-        while (ctl[kCtlReleased] < g + 1 - NS) {}
+        while (ctl[kCtlPublished] < g + 1 - NS) {}
+        if (t + 1 < ns) { // the compute warps decode the next step's record while they run this one
+            const int g1 = g + 1;
+            mbar_wait(data_bar + g1 % NS, (unsigned)(g1 / NS) & 1u);
+        }
         TWP_MARK(2);
         const unsigned sb = smem_u32(smem + (size_t)st * T::kStageBytes);
         if (pos >= 0) {
@@ -510,6 +485,67 @@ __device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, 
                 rhs[i][c] = rhs1[i][c];
     }
     TWP_FLUSH(16, lane == 0 && pw == 0);
+}
+
+// ---- publisher warp: stores a step's results from the ring as soon as the compute warps are done with it ------
+// One lane per row (a step has at most 32 rows).  Rows another chunk polls first, with a strong store -- that store
+// is the hop from chunk to chunk; the rest of y (read by the upper sweep, a later kernel), the result vector and the
+// sentinels of the rows polled in the other sweep follow as plain stores.  Then the stage is free.  Inside the
+// compute warps the same stores cost ~140 cycles per step of a chain that is bound by its instruction count.
+template <int B, int S, bool ILU0, bool UPPER>
+__device__ __forceinline__ void tw_publisher(const TwArgs& a, unsigned char* smem, int g0, int ns, int lane)
+{
+    constexpr bool DINV = !(ILU0 && !UPPER);
+    using T = TwCfg<B, S, DINV, UPPER>;
+    constexpr int NS = T::kStages;
+    const unsigned smem_s = smem_u32(smem);
+    volatile int* ctl = reinterpret_cast<volatile int*>(smem + T::kCtlOff);
+    double* out = UPPER ? a.vpoll : a.tmp;
+    double* arm = UPPER ? a.tmp : a.vpoll; // lower: arm the upper sweep's records; upper: re-arm for the next apply
+    TWP_DECL;
+    for (int t = 0; t < ns; ++t) {
+        const int g = g0 + t, st = g % NS;
+        const unsigned sb = smem_s + (unsigned)st * T::kStageBytes;
+        while (ctl[kCtlReleased] < g + 1) {}
+        TWP_MARK(0);
+        const int q0 = lds_s32(sb + T::kHdrOff), count = lds_s32(sb + T::kHdrOff + 4);
+        const bool polled = (lds_s32(sb + T::kPubOff) >> lane) & 1, armed = (lds_s32(sb + T::kArmOff) >> lane) & 1;
+        if (lane < count && !TW_DBG(1)) {
+            const int q = q0 + lane;
+            const unsigned ra = smem_s + T::kRingOff + (unsigned)(q & (T::RING - 1)) * 32;
+            double x[B];
+            if constexpr (B == 1) {
+                x[0] = lds_f64(ra);
+            } else {
+                lds_v2(ra, x[0], x[1]);
+                if constexpr (B == 3)
+                    x[2] = lds_f64(ra + 16);
+                if constexpr (B == 4)
+                    lds_v2(ra + 16, x[2], x[B - 1]);
+            }
+            if (polled)
+                rec_store_strong<B>(out, (size_t)q, x);
+            else if (!UPPER)
+                rec_store_weak<B>(out, (size_t)q, x);
+            if (UPPER) {
+#pragma unroll
+                for (int c = 0; c < B; ++c)
+                    a.v[VIDX(a.n, q, c)] = x[c];
+            }
+            if (armed) {
+                double sx[B];
+#pragma unroll
+                for (int c = 0; c < B; ++c)
+                    sx[c] = sentinel();
+                rec_store_weak<B>(arm, (size_t)q, sx);
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+            ctl[kCtlPublished] = g + 1; // the stage may be refilled, the ring slots overwritten (8 steps from now at the earliest)
+        TWP_MARK(1);
+    }
+    TWP_FLUSH(28, lane == 0);
 }
 
 template <int B, int S, bool ILU0, bool UPPER>
@@ -561,8 +597,10 @@ __global__ void __launch_bounds__(kTwMaxThreads, 1) tw_sweep_kernel(TwArgs a)
             tw_compute<B, S, ILU0, UPPER>(a, smem, g, ns, warp, lane);
         else if (warp == T::NW)
             tw_loader<B, S, ILU0, UPPER>(a, smem, rec0, g, ns, lane);
+        else if (warp == T::NW + 1)
+            tw_publisher<B, S, ILU0, UPPER>(a, smem, g, ns, lane);
         else
-            tw_poller<B, S, ILU0, UPPER>(a, smem, rec0, g, ns, warp - T::NW - 1, npw, lane);
+            tw_poller<B, S, ILU0, UPPER>(a, smem, rec0, g, ns, warp - T::NW - 2, npw, lane);
         g += ns;
         __syncthreads(); // everybody has read the control words; the chunk is finished and published
     }
@@ -609,10 +647,12 @@ __global__ void __launch_bounds__(256) tw_fill_kernel(int nsteps, int upper, con
             }
         }
         unsigned char* rec = stream + (size_t)(upper ? nsteps - 1 - st : st) * T::kRecBytes;
-        double2* dst = reinterpret_cast<double2*>(rec + T::kValOff) + (size_t)(warp * T::NP) * 32 + lane;
+        if (rw < T::RPW) { // the record holds the working lanes only
+            double2* dst = reinterpret_cast<double2*>(rec + T::kValOff) + (size_t)(warp * T::NP) * T::LW + lane;
 #pragma unroll
-        for (int k = 0; k < T::NP; ++k)
-            dst[(size_t)k * 32] = make_double2(av[2 * k], av[2 * k + 1]);
+            for (int k = 0; k < T::NP; ++k)
+                dst[(size_t)k * T::LW] = make_double2(av[2 * k], av[2 * k + 1]);
+        }
     }
 }
 

@@ -386,6 +386,16 @@ class ISTLSolverB200:
 
     def solve(self, x) -> bool:
         self._solve_count += 1
+        if int(self.prm.get("verbosity", 0, int)) > 10:
+            # ISTLSolver::solve writes the system when verbosity > 10 (ISTLSolver.hpp:433-440 ->
+            # WriteSystemMatrixHelper.hpp:63-94, Dune::storeMatrixMarket); scripts/replay_system.py reads it back
+            from . import matrixmarket
+            import os
+            d = self.prm.get("b200.dump_dir", "reports", str)
+            os.makedirs(d, exist_ok=True)
+            M = self._flex.op.getmat()
+            matrixmarket.write_matrix(os.path.join(d, f"prob_{self._solve_count}_matrix_istl.mm"), M)
+            matrixmarket.write_vector(os.path.join(d, f"prob_{self._solve_count}_rhs_istl.mm"), np.asarray(self._rhs), M.b)
         self.result = self._flex.apply(x, self._rhs)
         self._iterations = self.result.iterations
         return self.checkConvergence(self.result)

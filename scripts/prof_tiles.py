@@ -26,10 +26,11 @@ fs = FlexibleSolver(MatrixAdapter(A), {"preconditioner": {"type": prec},
 info = fs.info()
 lib = _lib.lib()
 out = (C.c_ulonglong * 40)()
-names = {0: "compute: barrier waits, steps >= 8", 6: "compute: barrier waits, steps < 8", 1: "compute: the step's block",
-         2: "compute: named barrier + release", 3: "compute: publish", 7: "compute: first step's loads",
+names = {0: "compute: wait for the externals, steps >= 8", 6: "compute: wait for the externals, steps < 8", 1: "compute: the step's block",
+         2: "compute: named barrier + release", 7: "compute: first step's loads",
          8: "loader: prefetch", 9: "loader: wait for a free stage", 10: "loader: expect_tx + TMA",
-         16: "poll w0: lists, next rhs + sample", 17: "poll w0: poll loop", 18: "poll w0: wait for a free stage", 19: "poll w0: park + arrive"}
+         16: "poll w0: lists, next rhs + sample", 17: "poll w0: poll loop", 18: "poll w0: wait for a free stage + next record",
+         19: "poll w0: park + arrive", 28: "publisher: wait for the step", 29: "publisher: stores + release"}
 for what, name in ((4, "lower"), (5, "upper")):
     fs.time_kernel(what, 2, 3)
     lib.opmb200_prof_read(out, 1)

@@ -437,3 +437,25 @@ def test_replayed_dump_matches_the_oracle(tmp_path, fmt, schedule):
     line = [l for l in r.stdout.splitlines() if l.startswith('{"replay_check"')][-1]
     c = json.loads(line)["replay_check"]
     assert c["n"] == A.n and c["iterations"] == c["oracle_iterations"] and c["x_rel_err"] < 1e-10
+
+
+def test_verbosity_above_10_dumps_the_system(tmp_path, schedule):
+    """ISTLSolver::solve writes matrix and right-hand side when verbosity > 10 (ISTLSolver.hpp:433-440); the dump reads back
+    to the same system and replays to the same solution"""
+    from opm_simulators_b200 import matrixmarket
+
+    if schedule != "levels":
+        pytest.skip("schedule-independent")
+    s = generators.blackoil_system(5, 4, 3, b=3, seed=2)
+    A = s["A"]
+    o = opts("dilu", tol=1e-8)
+    o["verbosity"] = 11
+    o["b200"]["dump_dir"] = str(tmp_path)
+    solver = ISTLSolverB200(o)
+    solver.prepare(A, s["rhs"].copy())
+    x = np.zeros(A.n * 3)
+    assert solver.solve(x)
+    B = matrixmarket.read_matrix(str(tmp_path / "prob_1_matrix_istl.mm"))
+    rhs = matrixmarket.read_vector(str(tmp_path / "prob_1_rhs_istl.mm"))
+    assert B.b == 3 and np.array_equal(B.rowptr, A.rowptr) and np.array_equal(B.col, A.col)
+    assert np.array_equal(B.val, A.val) and np.array_equal(rhs, s["rhs"])

@@ -131,7 +131,7 @@ def test_step_tables_replay_the_dilu_apply(name, make, kw):
 def test_auto_schedule_picks_tiles_on_box_grids_only():
     box = generators.blackoil_system(12, 20, 8, b=3, seed=3, with_rhs=False)["A"]
     P = plan_tiles(box, schedule=2)
-    assert P["schedule"] == 1 and P["chunk_rows"] < 0 and P["R"] == 40 and P["S"] == (3, 3)
+    assert P["schedule"] == 1 and P["chunk_rows"] < 0 and P["R"] == 32 and P["S"] == (3, 3)
     irregular = generators.config("C2", scale=0.3, with_rhs=False)["A"]
     assert plan_tiles(irregular, schedule=2)["schedule"] == 0
     rng = np.random.default_rng(8)
