@@ -124,7 +124,8 @@ struct opmb200_solver {
     int schedule = 2;   // requested: 0 levels, 1 tiles, 2 auto (what was built: L.schedule_mode)
     int chunk_rows = 0; // > 0 contiguous chunks, 0 automatic, < 0 a tile shape
     int prefetch = 4;   // tile walkers: L2 look-ahead of the loader warp, in steps (<= 32)
-    int poll_warps = 4; // tile walkers: warps polling the dependencies that cross a chunk boundary (1..6)
+    int poll_warps = 4; // tile walkers: warps polling the dependencies that cross a chunk boundary (1..4)
+    int rhs_warps = 2;  // tile walkers: warps fetching the steps' right-hand sides (1..2)
     int debug = 0;      // OPMB200_TWDBG builds: timing experiments (wrong results)
     int ctas_per_sm = 1; // tile walkers: persistent CTAs per SM (1 or 2)
     int device = 0;
@@ -406,7 +407,8 @@ int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
         c.prefetch = s->prefetch;
         c.debug = s->debug;
         c.poll_warps = s->poll_warps;
-        const int threads = (kTwWarps + 2 + s->poll_warps) * 32; // compute, loader, publisher, poll warps
+        c.rhs_warps = s->rhs_warps;
+        const int threads = (kTwWarps + 2 + s->rhs_warps + s->poll_warps) * 32; // compute, loader, publisher, rhs, poll warps
         c.ticket = a.ticket;
         c.sc = a.sc;
         c.check_done = a.check_done;
@@ -617,6 +619,7 @@ int parse_options(opmb200_solver* s, const char* json)
         s->chunk_rows = prm.get<int>("b200.chunk_rows", 0);
         s->prefetch = std::max(0, std::min(32, prm.get<int>("b200.prefetch_steps", 4)));
         s->poll_warps = std::max(1, std::min(kTwMaxPollWarps, prm.get<int>("b200.poll_warps", 4)));
+        s->rhs_warps = std::max(1, std::min(kTwMaxRhsWarps, prm.get<int>("b200.rhs_warps", 2)));
         s->debug = prm.get<int>("b200.debug_timing", 0);
         s->register_host = prm.get<int>("b200.register_host_buffers", 1) != 0;
         s->ctas_per_sm = std::max(1, std::min(2, prm.get<int>("b200.ctas_per_sm", 1)));
@@ -1469,6 +1472,42 @@ int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, doubl
                                                                    + 16 * (N + 1) + 8 * N);
         return OPMB200_SUCCESS;
     }
+    if (what == 6) {
+        // experiment (timing only, results meaningless): the upper sweep with an SpMV running beside it on a second
+        // stream -- what would hiding the SpMV behind the latency-bound sweep cost the sweep?
+        const SweepArgs sa = sweep_args(s, s->vr.p, s->vy.p, 1, 0);
+        cudaStream_t s2, keep = s->stream;
+        cudaEvent_t em, ej;
+        CUDA_TRY(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&em));
+        CUDA_TRY(cudaEventCreate(&ej));
+        double total = 0;
+        for (int it = 0; it < warmup + reps; ++it) {
+            TRY(launch_sweep(s, sa, false));
+            CUDA_TRY(cudaEventRecord(em, s->stream));
+            TRY(launch_sweep(s, sa, true));
+            CUDA_TRY(cudaStreamWaitEvent(s2, em, 0));
+            s->stream = s2;
+            const int rc = launch_spmv(s, s->vp.p, s->vv.p, false, 0.0, 0, nullptr, nullptr, EPI_NONE, 0);
+            s->stream = keep;
+            TRY(rc);
+            CUDA_TRY(cudaEventRecord(ej, s2));
+            CUDA_TRY(cudaStreamWaitEvent(s->stream, ej, 0));
+            CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            float ms = 0;
+            CUDA_TRY(cudaEventElapsedTime(&ms, em, s->ev1));
+            if (it >= warmup)
+                total += ms;
+        }
+        cudaEventDestroy(em);
+        cudaEventDestroy(ej);
+        cudaStreamDestroy(s2);
+        *ms_per_launch = total / reps;
+        if (algorithmic_bytes)
+            *algorithmic_bytes = 0;
+        return OPMB200_SUCCESS;
+    }
     for (int it = 0; it < warmup + reps; ++it) {
         if (it == warmup)
             CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
@@ -1515,9 +1554,9 @@ int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, doubl
 extern "C" int opmb200_prof_read(unsigned long long* out32, int reset)
 {
     cudaDeviceSynchronize();
-    cudaMemcpyFromSymbol(out32, g_twp, sizeof(unsigned long long) * 40);
+    cudaMemcpyFromSymbol(out32, g_twp, sizeof(unsigned long long) * 64);
     if (reset) {
-        unsigned long long z[40] = {0};
+        unsigned long long z[64] = {0};
         cudaMemcpyToSymbol(g_twp, z, sizeof z);
     }
     return 0;

@@ -28,10 +28,18 @@
 
 namespace opmb200 {
 
-constexpr int kTwMaxPollWarps = 6;
-// launch bound: compute warps, loader, publisher, poll warps; the launch picks the poll warps.  ONE CTA per SM: two
-// co-resident tile walkers slow each other down by more than they gain (C3: 250 us with two per SM, 205 us with one)
-constexpr int kTwMaxThreads = (kTwWarps + 2 + kTwMaxPollWarps) * 32;
+constexpr int kTwMaxPollWarps = 4;
+constexpr int kTwMaxRhsWarps = 2;
+// launch bound: compute warps, loader, publisher, right-hand-side warps, poll warps; the launch picks the last two.
+// ONE CTA per SM: two co-resident tile walkers slow each other down by more than they gain (C3: 250 us with two
+// per SM, 205 us with one)
+constexpr int kTwMaxThreads = (kTwWarps + 2 + kTwMaxRhsWarps + kTwMaxPollWarps) * 32;
+#ifndef TW_NO_EARLY_TEST
+#define TW_NO_EARLY_TEST 0
+#endif
+#ifndef TW_EXT_FLAG
+#define TW_EXT_FLAG 0 // 1: "externals parked" is a pair of shared-memory words the compute warps spin on, 0: an mbarrier
+#endif
 
 template <int B, int S, bool DINV, bool UPPER>
 struct TwCfg {
@@ -66,9 +74,12 @@ struct TwCfg {
     static constexpr int kStages = kStagesRaw < 2 ? 2 : (kStagesRaw > kStagesCap ? kStagesCap : kStagesRaw);
     static constexpr int kRingOff = kStages * kStageBytes;           // [RING][4] doubles
     static constexpr int kZeroOff = kRingOff + RING * 32;            // one all-zero record
-    static constexpr int kBarOff = kZeroOff + 32;                    // kStages "data", then kStages "ext" mbarriers
+    static constexpr int kScratchOff = kZeroOff + 32;                // where idle lanes and rows beyond a step's count store
+    static constexpr int kBarOff = kScratchOff + 32;                 // kStages "data", then kStages "ext" mbarriers
     static constexpr int kCtlOff = kBarOff + 16 * kStages;           // int[8], see TwCtl
-    static constexpr int kSmemBytes = kCtlOff + 32;
+    static constexpr int kFlagOff = kCtlOff + 32;                    // [kStages][2] step tokens: right-hand side parked, externals parked
+    static constexpr int kStampOff = kFlagOff + 8 * kStages;         // OPMB200_PROFILE: [kStages][2] arrival times (clock64)
+    static constexpr int kSmemBytes = kStampOff + 16 * kStages + 16;
 };
 // control words in shared memory
 enum TwCtl { kCtlReleased = 0, kCtlRec0 = 1, kCtlSteps = 2, kCtlStop = 3, kCtlQ0 = 4, kCtlQ1 = 5, kCtlPublished = 6 };
@@ -88,6 +99,7 @@ struct TwArgs {
     int prefetch;                // L2 look-ahead of the loader, in steps
     int debug;                   // OPMB200_TWDBG builds only: timing experiments that switch parts off (wrong results)
     int poll_warps;
+    int rhs_warps;
     Ticket ticket;
     Scalars* sc;
     int check_done;
@@ -145,7 +157,17 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void* p, unsigned bytes)
 // in-kernel profile of the tile walkers: cycles per phase, accumulated in registers by lane 0 of one warp per
 // role and flushed per chunk.  g_twp[0..7] compute phases, [8..15] loader phases, [16..23] poll phases,
 // [24] steps, [25] chunks, [26] poll loads issued, [28..35] store warp phases
-__device__ unsigned long long g_twp[40];
+__device__ unsigned long long g_twp[64];
+// hop anatomy: [40] polled records found valid, [41] ns from the producer's store to the consumer's valid sample
+// (globaltimer stamps travel in the unused 4th word of a b = 3 record), [42] max of that, [43] steps published,
+// [44] cycles from the compute warps' release to the publisher's store, [45] blocked steps, [46] cycles from the
+// last arrival on the ext barrier to the compute warps' restart
+__device__ __forceinline__ unsigned long long twp_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 #define TWP_DECL long long twp_t0__ = clock64(); unsigned long long twp_acc__[8] = {0, 0, 0, 0, 0, 0, 0, 0}
 #define TWP_MARK(i)                                                                                                    \
     do {                                                                                                               \
@@ -176,6 +198,7 @@ template <int B, int S, int NP>
 struct TwStep {
     int q0, count, flags;
     unsigned xaddr[S]; // where dependency s is found (ring, the stage's external slots, the zero record)
+    double av[2 * NP]; // this lane's block values (+ Dinv): in registers a step early, off the dependent chain
 };
 
 // ---- compute warps -------------------------------------------------------------------------------
@@ -220,6 +243,9 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
             const int c = lds_s32(sb + code_o + (unsigned)(s * T::RP) * 4);
             N.xaddr[s] = ((c & kTwRing) ? ring_s : sb + T::kExtValOff) + (unsigned)(c & (2 * T::RING - 1)) * 32;
         }
+#pragma unroll
+        for (int k = 0; k < T::NP; ++k)
+            lds_v2(sb + val_o + (unsigned)k * T::LW * 16, N.av[2 * k], N.av[2 * k + 1]);
     };
 
     int st = g0 % NS;
@@ -229,6 +255,7 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
     look_ahead(st, SA);
     TWP_MARK(7);
 
+    bool ext_ready = false;
     auto step = [&](int t, const Step& C, Step& N) {
         const int g = g0 + t;
         int st1 = st + 1;
@@ -240,7 +267,34 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
         // ---- what may loop first: ONE barrier ---------------------------------------------------------
         // this step's right-hand side and externals are parked -- and the poll warp that says so has seen the NEXT
         // step's record land (a second test of a completed phase here cost ~100 cycles per step)
-        mbar_wait(ext_bar + st, par);
+#if TW_EXT_FLAG
+        {
+            const unsigned fa = smem_s + T::kFlagOff + (unsigned)st * 8;
+            int f0, f1;
+            do {
+                asm volatile("ld.volatile.shared.v2.s32 {%0,%1}, [%2];" : "=r"(f0), "=r"(f1) : "r"(fa) : "memory");
+            } while (f0 != g + 1 || f1 != g + 1);
+        }
+#else
+#ifdef OPMB200_PROFILE
+        const long long tw0__ = clock64();
+#endif
+        if (!ext_ready) // (tested while the step before ran: a test of a completed phase costs 130-200 cycles)
+            mbar_wait(ext_bar + st, par);
+#endif
+#ifdef OPMB200_PROFILE
+        if (warp == 0 && lane == 0 && t >= 8) { // who was the step waiting for?  [36] rhs late, [37] externals late: counts; [38], [39]: cycles
+            const long long tr = reinterpret_cast<volatile long long*>(smem + T::kStampOff)[st * 2];
+            const long long te = reinterpret_cast<volatile long long*>(smem + T::kStampOff)[st * 2 + 1];
+            const long long last = tr > te ? tr : te;
+            if (last > tw0__) {
+                atomicAdd(&g_twp[tr > te ? 36 : 37], 1ull);
+                atomicAdd(&g_twp[tr > te ? 38 : 39], (unsigned long long)(last - tw0__));
+                atomicAdd(&g_twp[45], 1ull);
+                atomicAdd(&g_twp[46], (unsigned long long)(clock64() - last));
+            }
+        }
+#endif
         TWP_MARK(t < 8 ? 6 : 0);
         // ---- the step proper: one basic block ------------------------------------------------------
         double x[S][B];
@@ -256,16 +310,31 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
                     lds_v2(C.xaddr[s] + 16, x[s][2], x[s][B - 1]);
             }
         }
-        // this lane's block values (+ Dinv) and right-hand side: the record landed a step ago at the latest
+        // this lane's right-hand side (its block values came with the look-ahead of the step before)
         const unsigned sb0 = smem_s + (unsigned)st * T::kStageBytes;
-        double av[2 * T::NP];
-#pragma unroll
-        for (int k = 0; k < T::NP; ++k)
-            lds_v2(sb0 + val_o + (unsigned)k * T::LW * 16, av[2 * k], av[2 * k + 1]);
+        const double(&av)[2 * T::NP] = C.av;
         double in = lds_f64(sb0 + in_o);
         in = (zero_ghosts && (C.flags & 1)) ? 0.0 : in; // ParallelOverlappingILU0 never touches ghost rows
         look_ahead(st1, N);
+#if !TW_EXT_FLAG
+        // are the next step's right-hand side and externals parked already?  The answer travels while the chain runs
+        ext_ready = (t + 1 < ns) && !TW_NO_EARLY_TEST && mbar_test_wait(ext_bar + st1, par1);
+#endif
         // the row: same blocks, same order of operations as sweep_kernel
+#ifdef TW_EXPERIMENT_PRESCALED // timing experiment: pre-scaled blocks, three short chains, no shuffle round (wrong results)
+        double acc[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            acc[s] = s == 0 ? in : 0.0;
+#pragma unroll
+            for (int c = 0; c < B; ++c)
+                acc[s] -= av[s * B + c] * x[s][c];
+        }
+        double res = acc[0];
+#pragma unroll
+        for (int s = 1; s < S; ++s)
+            res += acc[s];
+#else
         double tsum = (UPPER && !ILU0) ? 0.0 : in;
 #pragma unroll
         for (int s = 0; s < S; ++s)
@@ -296,13 +365,18 @@ __device__ __forceinline__ void tw_compute(const TwArgs& a, unsigned char* smem,
         } else {
             res = tsum; // ILU0 lower: L_ii = I
         }
+#endif
         res = guard(res);
+        // (no branch: a divergent store costs a reconvergence per step; lanes without a row store into a scratch record)
         const bool active = lane_ok && rho < C.count;
         const int q = C.q0 + rho;
-        if (active)
-            sts_f64(ring_s + (unsigned)(q & (T::RING - 1)) * 32 + r * 8, res);
+        sts_f64((active ? ring_s + (unsigned)(q & (T::RING - 1)) * 32 : smem_s + T::kScratchOff) + r * 8, res);
         TWP_MARK(1);
         named_bar_sync(1, T::NW * 32); // the ring writes are visible to the four warps; everybody is done with the stage
+#ifdef OPMB200_PROFILE
+        if (threadIdx.x == 0)
+            reinterpret_cast<volatile long long*>(smem + T::kStampOff)[2 * NS] = clock64();
+#endif
         if (threadIdx.x == 0)
             ctl[kCtlReleased] = g + 1; // the publisher warp stores the step's results from the ring and frees the stage
         TWP_MARK(2);
@@ -364,26 +438,41 @@ __device__ __forceinline__ void tw_loader(const TwArgs& a, unsigned char* smem, 
     TWP_FLUSH(8, true);
 }
 
-// ---- poll warps: the dependencies the chunk's ring does not serve ---------------------------------------
+// "step g's right-hand side / externals are parked in stage st": one arrival on the stage's "ext" mbarrier, or a
+// shared-memory word (the lanes' stores ordered in front of it)
+template <class T>
+__device__ __forceinline__ void tw_signal(unsigned char* smem, int st, int g, int which, int lane)
+{
+    __syncwarp();
+    if (lane == 0) {
+#ifdef OPMB200_PROFILE
+        reinterpret_cast<volatile long long*>(smem + T::kStampOff)[st * 2 + which] = clock64();
+#endif
+#if TW_EXT_FLAG
+        __threadfence_block();
+        asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(smem_u32(smem) + T::kFlagOff + (unsigned)(st * 8 + which * 4)), "r"(g + 1) : "memory");
+#else
+        unsigned long long* ext_bar = reinterpret_cast<unsigned long long*>(smem + T::kBarOff) + T::kStages;
+        mbar_arrive(ext_bar + st); // release: the stores above are visible to whoever passes the barrier
+#endif
+    }
+}
+
+// ---- right-hand-side warps, each serving every n-th step: the step's right-hand side (from the solver vector or the
+// lower sweep's records, in the L2 since the chunk started), loaded one own-step ahead, parked in the stage ----------
 template <int B, int S, bool ILU0, bool UPPER>
-__device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, int rec0, int g0, int ns, int pw, int npw, int lane)
+__device__ __forceinline__ void tw_rhs(const TwArgs& a, unsigned char* smem, int rec0, int g0, int ns, int pw, int npw, int lane)
 {
     constexpr bool DINV = !(ILU0 && !UPPER);
     using T = TwCfg<B, S, DINV, UPPER>;
     constexpr int NS = T::kStages;
     unsigned long long* data_bar = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
-    unsigned long long* ext_bar = data_bar + NS;
     volatile int* ctl = reinterpret_cast<volatile int*>(smem + T::kCtlOff);
-    const double* out = UPPER ? a.vpoll : a.tmp;
     const unsigned char* rec = a.stream + (size_t)(rec0 + pw) * T::kRecBytes;
     constexpr int NR = (T::R + 31) / 32;      // rows per lane
     constexpr int NC = UPPER ? T::W : B;      // right-hand side words per row
-    // A round trip to the L2 is 1-3 thousand cycles under load and a warp serves every npw-th step.  So the
-    // header and external list of this warp's step after next, and the right-hand side plus a first SAMPLE of the
-    // dependencies of its next step travel while this step is served (a sample that finds the sentinel is repeated).
-    auto load_head = [&](const unsigned char* r, int4& hdr, int& pos) {
+    auto load_head = [&](const unsigned char* r, int4& hdr) {
         hdr = __ldg(reinterpret_cast<const int4*>(r)); // q0, count, n_ext, flags
-        pos = __ldg(reinterpret_cast<const int*>(r + T::kExtPosOff) + lane);
     };
     auto load_rhs = [&](const int4& hdr, double (&rhs)[NR][NC]) {
 #pragma unroll
@@ -413,51 +502,28 @@ __device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, 
         }
     };
     int4 hdr = make_int4(0, 0, 0, 0), hdr1 = hdr, hdr2 = hdr;
-    int pos = -1, pos1 = -1, pos2 = -1;
-    double rhs[NR][NC], rhs1[NR][NC], x[B], x1[B];
+    double rhs[NR][NC], rhs1[NR][NC];
     if (pw < ns) {
-        load_head(rec, hdr, pos);
+        load_head(rec, hdr);
         load_rhs(hdr, rhs);
-        if (pos >= 0)
-            rec_load_strong<B>(out, (size_t)pos, x);
     }
     if (pw + npw < ns)
-        load_head(rec + (size_t)npw * T::kRecBytes, hdr1, pos1);
+        load_head(rec + (size_t)npw * T::kRecBytes, hdr1);
     TWP_DECL;
     for (int t = pw; t < ns; t += npw, rec += (size_t)npw * T::kRecBytes) {
         const int g = g0 + t, st = g % NS;
         if (t + 2 * npw < ns)
-            load_head(rec + (size_t)2 * npw * T::kRecBytes, hdr2, pos2);
-        if (t + npw < ns) { // the next step this warp serves
+            load_head(rec + (size_t)2 * npw * T::kRecBytes, hdr2);
+        if (t + npw < ns) // the next step this warp serves
             load_rhs(hdr1, rhs1);
-            if (pos1 >= 0)
-                rec_load_strong<B>(out, (size_t)pos1, x1);
-        }
         TWP_MARK(0);
-        if (pos >= 0) {
-            int tries = 0;
-            // every word validates itself against the sentinel.  No nap between the samples, not even at chunk start:
-            // the first step's wait IS the hop from chunk to chunk, and a __nanosleep costs about a microsecond
-            while (!rec_valid<B>(x) && !TW_DBG(2)) {
-                ++tries;
-                rec_load_strong<B>(out, (size_t)pos, x);
-            }
-            TWP_COUNT(26, lane == 0 && pw == 0, tries);
-        }
-        __syncwarp();
-        TWP_MARK(1);
         while (ctl[kCtlPublished] < g + 1 - NS) {}
         if (t + 1 < ns) { // the compute warps decode the next step's record while they run this one
             const int g1 = g + 1;
             mbar_wait(data_bar + g1 % NS, (unsigned)(g1 / NS) & 1u);
         }
-        TWP_MARK(2);
+        TWP_MARK(1);
         const unsigned sb = smem_u32(smem + (size_t)st * T::kStageBytes);
-        if (pos >= 0) {
-#pragma unroll
-            for (int c = 0; c < B; ++c)
-                sts_f64(sb + T::kExtValOff + lane * 32 + c * 8, x[c]);
-        }
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
             const int rho = lane + 32 * i;
@@ -467,22 +533,79 @@ __device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, 
                     sts_f64(sb + T::kRhsOff + (unsigned)(UPPER ? rho * T::W + c : c * T::RP + rho) * 8, rhs[i][c]);
             }
         }
-        __syncwarp();
-        if (lane == 0)
-            mbar_arrive(ext_bar + st); // release: the stores above are visible to whoever passes the barrier
-        TWP_MARK(3);
+        tw_signal<T>(smem, st, g, 0, lane);
+        TWP_MARK(2);
         hdr1 = hdr2;
-        pos = pos1;
-        pos1 = pos2;
-        pos2 = -1;
-#pragma unroll
-        for (int c = 0; c < B; ++c)
-            x[c] = x1[c];
 #pragma unroll
         for (int i = 0; i < NR; ++i)
 #pragma unroll
             for (int c = 0; c < NC; ++c)
                 rhs[i][c] = rhs1[i][c];
+    }
+    TWP_FLUSH(32, lane == 0 && pw == 0);
+}
+
+// ---- poll warps, each serving every n-th step: the dependencies the chunk's ring does not serve, one lane per
+// dependency: strong loads of the sentinel-armed records (as in sweep_kernel) until they are valid.  Nothing else is in
+// flight in these warps -- a sample that waits behind other loads is a longer hop from chunk to chunk -- and the list
+// of positions comes from the step's record in shared memory.
+template <int B, int S, bool ILU0, bool UPPER>
+__device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, int g0, int ns, int pw, int npw, int lane)
+{
+    constexpr bool DINV = !(ILU0 && !UPPER);
+    using T = TwCfg<B, S, DINV, UPPER>;
+    constexpr int NS = T::kStages;
+    unsigned long long* data_bar = reinterpret_cast<unsigned long long*>(smem + T::kBarOff);
+    volatile int* ctl = reinterpret_cast<volatile int*>(smem + T::kCtlOff);
+    const double* out = UPPER ? a.vpoll : a.tmp;
+    TWP_DECL;
+    for (int t = pw; t < ns; t += npw) {
+        const int g = g0 + t, st = g % NS;
+        const unsigned sb = smem_u32(smem + (size_t)st * T::kStageBytes);
+        // the stage's previous step is done with (so its record HAS landed: a parity wait is only meaningful
+        // against the phase right before -- a warp that serves every n-th step does not see every phase), then
+        // this step's record: its list of positions is there
+        while (ctl[kCtlPublished] < g + 1 - NS) {}
+        mbar_wait(data_bar + st, (unsigned)(g / NS) & 1u);
+        const int pos = lds_s32(sb + T::kExtPosOff + lane * 4);
+        TWP_MARK(0);
+        if (pos >= 0 && !TW_DBG(2)) {
+            double x[B];
+            int tries = 0;
+            // every word validates itself against the sentinel.  No nap between the samples: the wait IS the hop from
+            // chunk to chunk, and a __nanosleep costs about a microsecond
+#ifdef OPMB200_PROFILE
+            if constexpr (B == 3) {
+                double w3;
+                do {
+                    ++tries;
+                    asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+                                 : "=d"(x[0]), "=d"(x[1]), "=d"(x[B - 1]), "=d"(w3)
+                                 : "l"(out + (size_t)pos * 4)
+                                 : "memory");
+                } while (!rec_valid<B>(x));
+                if (tries > 1) { // the hops that were waited for
+                    const unsigned long long dt = twp_globaltimer() - (unsigned long long)__double_as_longlong(w3);
+                    if (dt < 1000000ull) {
+                        atomicAdd(&g_twp[40], 1ull);
+                        atomicAdd(&g_twp[41], dt);
+                        atomicMax(&g_twp[42], dt);
+                    }
+                }
+            } else
+#endif
+            do {
+                ++tries;
+                rec_load_strong<B>(out, (size_t)pos, x);
+            } while (!rec_valid<B>(x));
+            TWP_COUNT(26, lane == 0 && pw == 0, tries);
+#pragma unroll
+            for (int c = 0; c < B; ++c)
+                sts_f64(sb + T::kExtValOff + lane * 32 + c * 8, x[c]);
+        }
+        TWP_MARK(1);
+        tw_signal<T>(smem, st, g, 1, lane);
+        TWP_MARK(2);
     }
     TWP_FLUSH(16, lane == 0 && pw == 0);
 }
@@ -506,10 +629,19 @@ __device__ __forceinline__ void tw_publisher(const TwArgs& a, unsigned char* sme
     for (int t = 0; t < ns; ++t) {
         const int g = g0 + t, st = g % NS;
         const unsigned sb = smem_s + (unsigned)st * T::kStageBytes;
-        while (ctl[kCtlReleased] < g + 1) {}
-        TWP_MARK(0);
+        // the step's header before the wait for its results (the record landed while the compute warps were busy
+        // with the step before)
+        mbar_wait(reinterpret_cast<unsigned long long*>(smem + T::kBarOff) + st, (unsigned)(g / NS) & 1u);
         const int q0 = lds_s32(sb + T::kHdrOff), count = lds_s32(sb + T::kHdrOff + 4);
         const bool polled = (lds_s32(sb + T::kPubOff) >> lane) & 1, armed = (lds_s32(sb + T::kArmOff) >> lane) & 1;
+        while (ctl[kCtlReleased] < g + 1) {}
+#ifdef OPMB200_PROFILE
+        if (lane == 0) {
+            atomicAdd(&g_twp[43], 1ull);
+            atomicAdd(&g_twp[44], (unsigned long long)(clock64() - reinterpret_cast<volatile long long*>(smem + T::kStampOff)[2 * NS]));
+        }
+#endif
+        TWP_MARK(0);
         if (lane < count && !TW_DBG(1)) {
             const int q = q0 + lane;
             const unsigned ra = smem_s + T::kRingOff + (unsigned)(q & (T::RING - 1)) * 32;
@@ -523,6 +655,14 @@ __device__ __forceinline__ void tw_publisher(const TwArgs& a, unsigned char* sme
                 if constexpr (B == 4)
                     lds_v2(ra + 16, x[2], x[B - 1]);
             }
+#ifdef OPMB200_PROFILE
+            if (polled && B == 3) {
+                double* pr = out + (size_t)q * 4;
+                asm volatile("st.relaxed.gpu.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(pr), "d"(x[0]), "d"(x[1]), "d"(x[B - 1]),
+                             "d"(__longlong_as_double((long long)twp_globaltimer()))
+                             : "memory");
+            } else
+#endif
             if (polled)
                 rec_store_strong<B>(out, (size_t)q, x);
             else if (!UPPER)
@@ -560,10 +700,10 @@ __global__ void __launch_bounds__(kTwMaxThreads, 1) tw_sweep_kernel(TwArgs a)
     if (threadIdx.x == 0) {
         for (int i = 0; i < T::kStages; ++i) {
             mbar_init(bars + i, 1u);                // data: the loader's expect_tx
-            mbar_init(bars + T::kStages + i, 1u);   // ext: the poll warp
+            mbar_init(bars + T::kStages + i, 2u);   // ext: the right-hand-side warp and the poll warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 8 + 2 * T::kStages; ++i) // control words and step tokens
             ctl[i] = 0;
     }
     // idle lanes, rows beyond a step's count and the look-ahead behind a chunk's last step read words nobody
@@ -573,7 +713,7 @@ __global__ void __launch_bounds__(kTwMaxThreads, 1) tw_sweep_kernel(TwArgs a)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic writes before the TMA writes
     __syncthreads();
     const bool skip = a.check_done && a.sc->done;
-    const int npw = a.poll_warps;
+    const int npw = a.poll_warps, nrw = a.rhs_warps;
     int g = 0; // steps walked by this CTA so far: stage = g % kStages, phase = (g / kStages) & 1
     for (;;) {
         if (threadIdx.x == 0) {
@@ -599,8 +739,10 @@ __global__ void __launch_bounds__(kTwMaxThreads, 1) tw_sweep_kernel(TwArgs a)
             tw_loader<B, S, ILU0, UPPER>(a, smem, rec0, g, ns, lane);
         else if (warp == T::NW + 1)
             tw_publisher<B, S, ILU0, UPPER>(a, smem, g, ns, lane);
+        else if (warp < T::NW + 2 + nrw)
+            tw_rhs<B, S, ILU0, UPPER>(a, smem, rec0, g, ns, warp - T::NW - 2, nrw, lane);
         else
-            tw_poller<B, S, ILU0, UPPER>(a, smem, rec0, g, ns, warp - T::NW - 2, npw, lane);
+            tw_poller<B, S, ILU0, UPPER>(a, smem, g, ns, warp - T::NW - 2 - nrw, npw, lane);
         g += ns;
         __syncthreads(); // everybody has read the control words; the chunk is finished and published
     }

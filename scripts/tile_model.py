@@ -23,7 +23,8 @@ for dims in grids:
         t0 = time.time()
         fs = FlexibleSolver(MatrixAdapter(A), {"preconditioner": {"type": os.environ.get("PREC", "dilu")},
                                               "b200": {"schedule": "tiles", "poll_warps": int(pw), "prefetch_steps": int(pf),
-                                                       "debug_timing": int(dbg), "ctas_per_sm": int(os.environ.get("CPS", "2"))}})
+                                                       "debug_timing": int(dbg), "ctas_per_sm": int(os.environ.get("CPS", "1")),
+                                                       "chunk_rows": int(os.environ.get("TILE", "0"))}})
         info = fs.info()
         t1 = time.time()
         lo, _ = fs.time_kernel(4, 3, 10)
