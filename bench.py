@@ -53,45 +53,82 @@ def peaks():
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """samples SM clocks / throttle reasons while the timed region runs: NVML in a thread every 5 ms (the timed
+    region of the default run is ~150 ms: an `nvidia-smi -lms` child process would not have started by then);
+    falls back to one `nvidia-smi` query if NVML is not importable"""
+    REASONS = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
 
     def __init__(self, device_index: int):
         self.dev = device_index
-        self.rows = []
-        self.proc = None
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        self._h = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            # torch's device ordinal follows CUDA_VISIBLE_DEVICES; NVML's does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = device_index
+            if vis:
+                try:
+                    idx = int(vis.split(",")[device_index])
+                except ValueError:
+                    idx = device_index
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._h = None
+
+    def _sample(self):
+        nv = self._nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        for name, bit in self.REASONS:
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            self._stop.wait(0.005)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.dev)], stdout=subprocess.PIPE, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+        if self._h is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
 
     def stop(self):
-        if self.proc:
-            self.proc.terminate()
+        if self._thread:
+            if not self.sm:  # a region shorter than the first sample: take one now, still under load
+                try:
+                    self._sample()
+                except Exception:
+                    pass
+            self._stop.set()
+            self._thread.join(timeout=2)
+        elif self._h is None:
             try:
-                self.proc.wait(timeout=2)
+                q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+                    "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.dev)],
+                                   capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+                self.sm, self.max_mhz = [float(r[0])], float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(name)
             except Exception:
-                self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 9:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                pass
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def workload(config, rank, world, nz_per_rank=None, seed_shift=0):
@@ -268,12 +305,19 @@ def reduced_parity(D, args, comm):
     return out
 
 
+_WORKLOADS = {}
+
+
 def measure_config(D, args, comm, name, config, nz_per_rank, prec, steps, warmup):
     """one extra multi-GPU configuration: device-resident steps + per-rank kernel times + correctness"""
     import torch
 
     t0 = time.perf_counter()
-    w = workload(config, D.rank, D.world, nz_per_rank=nz_per_rank)
+    key = (config, nz_per_rank)
+    if key not in _WORKLOADS:  # DILU and ILU0 of a configuration share the generated slab
+        _WORKLOADS.clear()
+        _WORKLOADS[key] = workload(config, D.rank, D.world, nz_per_rank=nz_per_rank)
+    w = _WORKLOADS[key]
     t_gen = time.perf_counter() - t0
     fs = make_solver(D, w, prec, args.tol, args.collectives, comm)
     info = fs.info()
@@ -437,7 +481,10 @@ def run_b200(args):
         configs = {}
         for name, config, nzr in (("C4", "C4", 50), ("C5", "C5", 25)):
             for prec in ("dilu", "ilu0"):
-                configs[f"{name}_{prec}"] = measure_config(D, args, comm, name, config, nzr, prec, 3, 2)
+                try:
+                    configs[f"{name}_{prec}"] = measure_config(D, args, comm, name, config, nzr, prec, 3, 2)
+                except Exception as e:  # an extra configuration must not cost the headline line
+                    configs[f"{name}_{prec}"] = {"error": repr(e)[:200]}
 
     out = None
     steps = args.steps
@@ -479,6 +526,7 @@ def run_b200(args):
             out["per_rank"] = per_rank
         if configs:
             out["configs"] = configs
+        _WORKLOADS.clear()
     # ---- CPU baseline (rank 0, single-GPU run only) -------------------------------------------------------
     if rank == 0 and world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_port_baseline(w, args)

@@ -29,7 +29,7 @@
 namespace opmb200 {
 
 constexpr int kTwMaxPollWarps = 4;
-constexpr int kTwMaxRhsWarps = 2;
+constexpr int kTwMaxRhsWarps = 4;
 // launch bound: compute warps, loader, publisher, right-hand-side warps, poll warps; the launch picks the last two.
 // ONE CTA per SM: two co-resident tile walkers slow each other down by more than they gain (C3: 250 us with two
 // per SM, 205 us with one)

@@ -16,9 +16,10 @@ prec = sys.argv[3] if len(sys.argv) > 3 else "dilu"
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 what = sys.argv[5] if len(sys.argv) > 5 else "apply"
 scale = float(os.environ.get("SCALE", "1.0"))
-s = generators.config(cfg, scale=scale)
+dims = os.environ.get("DIMS")  # e.g. 1000x8x4: one free-running tile
+s = generators.blackoil_system(*[int(v) for v in dims.split("x")], b=3, seed=5) if dims else generators.config(cfg, scale=scale)
 A = s["A"]
-fs = FlexibleSolver(MatrixAdapter(A), {"tol": 1e-2, "preconditioner": {"type": prec}, "b200": {"schedule": sched}})
+fs = FlexibleSolver(MatrixAdapter(A), {"tol": 1e-2, "preconditioner": {"type": prec}, "b200": {"schedule": sched, "chunk_rows": int(os.environ.get("CHUNK_ROWS", "0"))}})
 d = s["rhs2"]
 if what == "apply":
     for _ in range(reps):
