@@ -129,7 +129,7 @@ int opmb200_plan_schedule(int block_size, int64_t n_rows, int64_t nnzb, const in
  * n_chunks, chunk_rows}.  With info[0] == 1 and non-NULL pointers: step_first[n_steps+1] positions,
  * chunk_first_step[n_chunks+1], step_flags[n_steps] (bit 0: ghost rows) and, for `direction` (0 lower,
  * 1 upper) with S slots and RP = (R+3)&~3: codes[n_steps*S*RP] ((1<<30) + ring positions: none | (1<<30) + ring index |
- * (1<<29) + external slot), ext[n_steps*32] positions, n_ext[n_steps].  Call once with NULL arrays to size. */
+ * (1<<29) + external slot), ext[n_steps*64] positions, n_ext[n_steps].  Call once with NULL arrays to size. */
 int opmb200_plan_tiles(int block_size, int64_t n_rows, int64_t nnzb, const int32_t* rowptr, const int32_t* colidx,
                        int64_t n_interior, int schedule, int chunk_rows, int32_t* info, int32_t* position_to_row,
                        int32_t* step_first, int32_t* chunk_first_step, int32_t* step_flags, int direction,

@@ -25,7 +25,7 @@ namespace opmb200 {
 
 constexpr int kSlice = 32;
 constexpr int32_t kTwRing = 1 << 30, kTwExt = 1 << 29; // dependency codes of the tile walkers
-constexpr int kTwMaxExt = 32;                        // external dependencies per step (one per poll lane)
+constexpr int kTwMaxExt = 64;                        // external dependencies per step (two per poll lane)
 constexpr int kTwWarps = 4;                          // compute warps of a tile walker
 constexpr int kTwRows = 32;                          // rows of a step (one SELL slice): kTwWarps x 8 rows, b lanes each
 

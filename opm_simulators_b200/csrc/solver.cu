@@ -125,7 +125,7 @@ struct opmb200_solver {
     int chunk_rows = 0; // > 0 contiguous chunks, 0 automatic, < 0 a tile shape
     int prefetch = 4;   // tile walkers: L2 look-ahead of the loader warp, in steps (<= 32)
     int poll_warps = 4; // tile walkers: warps polling the dependencies that cross a chunk boundary (1..4)
-    int rhs_warps = 2;  // tile walkers: warps fetching the steps' right-hand sides (1..2)
+    int rhs_warps = 3;  // tile walkers: warps fetching the steps' right-hand sides (1..4)
     int debug = 0;      // OPMB200_TWDBG builds: timing experiments (wrong results)
     int ctas_per_sm = 1; // tile walkers: persistent CTAs per SM (1 or 2)
     int device = 0;
@@ -619,7 +619,7 @@ int parse_options(opmb200_solver* s, const char* json)
         s->chunk_rows = prm.get<int>("b200.chunk_rows", 0);
         s->prefetch = std::max(0, std::min(32, prm.get<int>("b200.prefetch_steps", 4)));
         s->poll_warps = std::max(1, std::min(kTwMaxPollWarps, prm.get<int>("b200.poll_warps", 4)));
-        s->rhs_warps = std::max(1, std::min(kTwMaxRhsWarps, prm.get<int>("b200.rhs_warps", 2)));
+        s->rhs_warps = std::max(1, std::min(kTwMaxRhsWarps, prm.get<int>("b200.rhs_warps", 3)));
         s->debug = prm.get<int>("b200.debug_timing", 0);
         s->register_host = prm.get<int>("b200.register_host_buffers", 1) != 0;
         s->ctas_per_sm = std::max(1, std::min(2, prm.get<int>("b200.ctas_per_sm", 1)));

@@ -567,9 +567,14 @@ __device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, 
         // this step's record: its list of positions is there
         while (ctl[kCtlPublished] < g + 1 - NS) {}
         mbar_wait(data_bar + st, (unsigned)(g / NS) & 1u);
-        const int pos = lds_s32(sb + T::kExtPosOff + lane * 4);
+        // one dependency per lane; a step with more than 32 of them (kTwMaxExt = 64: the steps of a rank's first plane
+        // also read the ghost plane below) takes a second round -- rare, and the ghost values are there already
+        const int n_ext = lds_s32(sb + T::kHdrOff + 8);
         TWP_MARK(0);
-        if (pos >= 0 && !TW_DBG(2)) {
+        for (int e0 = 0; e0 < n_ext && !TW_DBG(2); e0 += 32) {
+            const int pos = lds_s32(sb + T::kExtPosOff + (e0 + lane) * 4);
+            if (pos < 0)
+                continue;
             double x[B];
             int tries = 0;
             // every word validates itself against the sentinel.  No nap between the samples: the wait IS the hop from
@@ -598,10 +603,10 @@ __device__ __forceinline__ void tw_poller(const TwArgs& a, unsigned char* smem, 
                 ++tries;
                 rec_load_strong<B>(out, (size_t)pos, x);
             } while (!rec_valid<B>(x));
-            TWP_COUNT(26, lane == 0 && pw == 0, tries);
+            TWP_COUNT(26, lane == 0 && pw == 0 && e0 == 0, tries);
 #pragma unroll
             for (int c = 0; c < B; ++c)
-                sts_f64(sb + T::kExtValOff + lane * 32 + c * 8, x[c]);
+                sts_f64(sb + T::kExtValOff + (e0 + lane) * 32 + c * 8, x[c]);
         }
         TWP_MARK(1);
         tw_signal<T>(smem, st, g, 1, lane);

@@ -32,13 +32,13 @@ def plan_tiles(A, schedule=1, chunk_rows=0, n_interior=None, direction=0):
     chunk_first = np.zeros(P["n_chunks"] + 1, np.int32)
     flags = np.zeros(P["n_steps"], np.int32)
     codes = np.zeros(P["n_steps"] * S * RP, np.int32)
-    ext = np.zeros(P["n_steps"] * 32, np.int32)
+    ext = np.zeros(P["n_steps"] * 64, np.int32)
     n_ext = np.zeros(P["n_steps"], np.int32)
     _lib.check(f(A.b, n, A.nnzb, A.rowptr, A.col, ni, schedule, chunk_rows, info.ctypes.data, r2n.ctypes.data,
                  step_first.ctypes.data, chunk_first.ctypes.data, flags.ctypes.data, direction, codes.ctypes.data,
                  ext.ctypes.data, n_ext.ctypes.data))
     P.update(step_first=step_first, chunk_first=chunk_first, flags=flags, codes=codes.reshape(P["n_steps"], S, RP),
-             ext=ext.reshape(P["n_steps"], 32), n_ext=n_ext, RP=RP)
+             ext=ext.reshape(P["n_steps"], 64), n_ext=n_ext, RP=RP)
     return P
 
 
@@ -61,7 +61,7 @@ def replay_dilu(A, Dinv, d, n_interior=None, **kw):
             steps = range(P["chunk_first"][c], P["chunk_first"][c + 1])
             for st in (steps if direction == 0 else reversed(steps)):
                 q0, q1 = P["step_first"][st], P["step_first"][st + 1]
-                assert 0 < q1 - q0 <= P["R"] and P["n_ext"][st] <= 32
+                assert 0 < q1 - q0 <= P["R"] and P["n_ext"][st] <= 64
                 extv = np.array([out[p] for p in P["ext"][st][: P["n_ext"][st]]]).reshape(-1, b)
                 assert not np.isnan(extv).any(), "an external dependency is produced later in ticket order"
                 res = np.zeros((q1 - q0, b))
@@ -84,7 +84,7 @@ def replay_dilu(A, Dinv, d, n_interior=None, **kw):
                             x = ring[code & (ring_n - 1)]
                         else:
                             assert code & EXT
-                            x = extv[code & 31]
+                            x = extv[code & 63]
                         assert not np.isnan(x).any()
                         if direction:
                             acc += A.val[ents[k]] @ x
