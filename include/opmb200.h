@@ -192,6 +192,39 @@ int opmb200_dot(opmb200_solver* s, const double* x, const double* y, double* res
  *    b: OVERWRITTEN with the final residual, as Dune does.  reduction < 0: use "tol". */
 int opmb200_solve(opmb200_solver* s, double* x, double* b, double reduction, opmb200_result* res);
 
+/* ---- standard wells kept outside the matrix (matrix-add-well-contributions=false, Flow's default) ----
+ * == WellModelMatrixAdapter / WellModelGhostLastMatrixAdapter (WellOperators.hpp:224-287, 300-360) around
+ *    WellModelAsLinearOperator::apply / applyscaleadd (:84-109, 144-164) -> StandardWellEquations::apply
+ *    (wells/StandardWellEquations.cpp:132-148); the reference's GPU twin is WellContributionsCuda::apply
+ *    (gpubridge/cuda/cuWellContributions.cu:37-130, 166-190).
+ * After this call every operator application of the handle (opmb200_solve's SpMVs, opmb200_op_apply,
+ * opmb200_op_applyscaleadd) is  (A - sum_w C_w^T D_w^-1 B_w) x ; the preconditioner stays that of A, as in Flow.
+ *   well_ptr[n_wells+1]  perforation range of every well;  cells[n_perf]  local row of each perforation
+ *   B, C   [n_perf][dim_wells][block_size] row-major (duneB_ / duneC_: one dim_wells x block_size block per
+ *          perforation; C is applied transposed),  Dinv [n_wells][dim_wells][dim_wells] (invDuneD_)
+ * All host arrays (the well equations live on the host); copied at every call, the index tables are rebuilt only
+ * when the structure changed.  n_wells == 0 removes the wells.  Call again after every well assembly. */
+int opmb200_set_wells(opmb200_solver* s, int n_wells, int dim_wells, const int32_t* well_ptr, const int32_t* cells,
+                      const double* B, const double* C, const double* Dinv);
+
+/* ---- CPR pieces either side of the ILU0/DILU smoother -------------------------------------------------
+ * All vectors in the caller's natural order, host or device pointers; `transpose` as in the reference
+ * (false: weights multiply the equations (rows), the default "quasiimpes"/"trueimpes" CPR; true: CPRT).
+ * == Amg::getQuasiImpesWeights (getQuasiImpesWeights.hpp:64-111; gpuistl/detail/cpr_amg_operations.cu:35-76):
+ *    weights[n*b] from the diagonal blocks of the values of the last opmb200_update_values */
+int opmb200_cpr_quasi_impes_weights(opmb200_solver* s, int pressure_index, int transpose, double* weights);
+/* == PressureTransferPolicy::calculateCoarseEntries (PressureTransferPolicy.hpp; cpr_amg_operations.cu:79-123):
+ *    coarse_values[k] for every block k of the caller's BCSR (blocks of ghost rows: 0) */
+int opmb200_cpr_coarse_entries(opmb200_solver* s, const double* weights, int pressure_index, int transpose,
+                               double* coarse_values);
+/* == PressureTransferPolicy::moveToCoarseLevel (cpr_amg_operations.cu:126-151): coarse[n] from fine[n*b] */
+int opmb200_cpr_restrict(opmb200_solver* s, const double* weights, int pressure_index, int transpose,
+                         const double* fine, double* coarse);
+/* == PressureTransferPolicy::moveToFineLevel (PressureTransferPolicy.hpp:148-162; cpr_amg_operations.cu:154-178):
+ *    transpose == false writes only the pressure component of fine[n*b] */
+int opmb200_cpr_prolongate(opmb200_solver* s, const double* weights, int pressure_index, int transpose,
+                           const double* coarse, double* fine);
+
 /* ---- introspection (parity tests) ---------------------------------------------------------- */
 int opmb200_get_info(opmb200_solver* s, opmb200_info* info);
 /* level sets exactly as getMatrixRowColoring(A, LOWER) returns them: level_ptr[n_levels+1],

@@ -224,6 +224,46 @@ inline std::shared_ptr<opmb200_comm> ncclFromMpi(const Comm& comm)
 }
 #endif
 
+// ---- wells kept outside the matrix (matrix-add-well-contributions=false) ----------------------------------
+// The flat form of every StandardWell's equations, which is what StandardWellEquations::extract hands the
+// reference's GPU bridge (wells/StandardWellEquations.cpp extract(WellContributions&) -> gpubridge/
+// WellContributions.cpp addMatrix): per perforation the perforated cell and one dimWells x blocksize block of duneB_
+// and duneC_, per well invDuneD_.  Fill it in BlackoilWellModel's loop over the wells after every well assembly and
+// hand it to Solver::setWells: the device operator becomes A - sum_w C_w^T D_w^-1 B_w (WellModelMatrixAdapter,
+// WellOperators.hpp:224-287) while getmat() -- and with it the preconditioner -- stays A.
+struct FlatWells {
+    int dimWells = 0;
+    std::vector<std::int32_t> ptr {0}, cells;
+    std::vector<double> B, C, Dinv;
+
+    // duneB / duneC: one-row BCRS matrices of dimWells x blocksize blocks over the well's perforations (column
+    // index = perforation), invDuneD: the dimWells x dimWells inverse block, wellCells[perforation] = local cell
+    template <class OffDiagMatrix, class DiagBlock, class Cells>
+    void addWell(const OffDiagMatrix& duneB, const OffDiagMatrix& duneC, const DiagBlock& invDuneD, const Cells& wellCells)
+    {
+        auto rowB = duneB.begin();
+        auto rowC = duneC.begin();
+        auto colC = rowC->begin();
+        for (auto colB = rowB->begin(); colB != rowB->end(); ++colB, ++colC) {
+            const auto& blkB = *colB;
+            const auto& blkC = *colC;
+            if (dimWells == 0)
+                dimWells = static_cast<int>(blkB.N());
+            cells.push_back(static_cast<std::int32_t>(wellCells[colB.index()]));
+            for (std::size_t r = 0; r < blkB.N(); ++r)
+                for (std::size_t c = 0; c < blkB.M(); ++c) {
+                    B.push_back(blkB[r][c]);
+                    C.push_back(blkC[r][c]);
+                }
+        }
+        for (int r = 0; r < dimWells; ++r)
+            for (int c = 0; c < dimWells; ++c)
+                Dinv.push_back(invDuneD[r][c]);
+        ptr.push_back(static_cast<std::int32_t>(cells.size()));
+    }
+    int numWells() const { return static_cast<int>(ptr.size()) - 1; }
+};
+
 // Dune::PreconditionerWithUpdate<X,Y> (PreconditionerWithUpdate.hpp:32-41)
 template <class Operator>
 class Preconditioner : public Dune::PreconditionerWithUpdate<typename Operator::domain_type, typename Operator::range_type>
@@ -306,6 +346,13 @@ public:
     {
         return h_->parallel() ? Dune::SolverCategory::overlapping : Dune::SolverCategory::sequential;
     }
+    // wells as a LinearOperatorExtra (WellModelMatrixAdapter): every operator application of apply() adds them
+    void setWells(const FlatWells& w)
+    {
+        Handle<Matrix>::check(opmb200_set_wells(h_->get(), w.numWells(), w.dimWells, w.ptr.data(), w.cells.data(),
+                                                w.B.data(), w.C.data(), w.Dinv.data()));
+    }
+    void clearWells() { Handle<Matrix>::check(opmb200_set_wells(h_->get(), 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr)); }
     // FlexibleSolver::preconditioner(): ISTLSolver calls .update() on it every Newton step
     Dune::PreconditionerWithUpdate<X, X>& preconditioner() { return *prec_; }
     std::shared_ptr<Handle<Matrix>> handle() const { return h_; }

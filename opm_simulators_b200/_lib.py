@@ -87,6 +87,11 @@ PROTOTYPES = {
     "opmb200_p2p_import": (C.c_int, [_vp, _vp]),
     "opmb200_timer_start": (C.c_int, [_vp]),
     "opmb200_timer_stop": (C.c_int, [_vp, C.POINTER(C.c_double)]),
+    "opmb200_set_wells": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp]),
+    "opmb200_cpr_quasi_impes_weights": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "opmb200_cpr_coarse_entries": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp]),
+    "opmb200_cpr_restrict": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
+    "opmb200_cpr_prolongate": (C.c_int, [_vp, _vp, C.c_int, C.c_int, _vp, _vp]),
 }
 
 _lib = None

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("OPMB200_LIB") or os.path.join(HERE, "libopmb200.so")
 SOURCES = ["solver.cu", "analysis.cpp"]
-DEPS = SOURCES + ["kernels.cuh", "tile_kernels.cuh", "layout.hpp", "../../include/opmb200.h", "../../include/opmb200/property_tree.hpp"]
+DEPS = SOURCES + ["kernels.cuh", "tile_kernels.cuh", "extra_kernels.cuh", "layout.hpp", "../../include/opmb200.h", "../../include/opmb200/property_tree.hpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 

@@ -744,9 +744,23 @@ struct SpmvArgs {
     double* hist;
     double* dot_out;
     int check_done;
+    // standard wells kept outside the matrix (WELLS instantiations only; well_z_kernel ran on x before):
+    //   well_head[q]: -1, or t with the perforations e in [well_ptr[t], well_ptr[t+1]) of the cell at position q
+    //   well_perf[e] = perforation (its C block: well_C[perf][dw][B]), well_of[e] = its well (z2 = Dinv B x: well_z[well][dw])
+    const int* well_head;
+    const int* well_ptr;
+    const int* well_perf;
+    const int* well_of;
+    const double* well_C;
+    const double* well_z;
+    int well_dw;
 };
 
-template <int B, bool SCALEADD, int NDOT>
+// WELLS: y = (A - C^T D^-1 B) x, the operator of WellModelMatrixAdapter / WellModelGhostLastMatrixAdapter
+// (WellOperators.hpp:244-262, 325-356; the reference's GPU twin is a separate kernel after the SpMV,
+// gpubridge/cuda/cuWellContributions.cu:37-130): the few perforated rows subtract C_p^T z_w in the order the
+// reference's wells visit them, inside the SpMV, so the fused dots see the corrected result.
+template <int B, bool SCALEADD, int NDOT, bool WELLS = false>
 __global__ void __launch_bounds__(kCtaThreads) spmv_kernel(SpmvArgs a)
 {
     constexpr int BB = B * B;
@@ -779,6 +793,22 @@ __global__ void __launch_bounds__(kCtaThreads) spmv_kernel(SpmvArgs a)
                 for (int r = 0; r < B; ++r)
                     xv[r] = __ldg(a.x + VIDX(a.n, c, r));
                 blk_umv<B>(blk, xv, acc);
+            }
+        }
+        if (WELLS && active) {
+            const int t = __ldg(a.well_head + q);
+            if (t >= 0) {
+                const int e1 = a.well_ptr[t + 1];
+                for (int e = a.well_ptr[t]; e < e1; ++e) {
+                    const double* Cp = a.well_C + (size_t)a.well_perf[e] * a.well_dw * B;
+                    const double* z = a.well_z + (size_t)a.well_of[e] * a.well_dw;
+                    for (int r = 0; r < a.well_dw; ++r) { // BCRSMatrix::mmtv: y[c] -= C[r][c] z[r]
+                        const double zr = z[r];
+#pragma unroll
+                        for (int c = 0; c < B; ++c)
+                            acc[c] -= Cp[r * B + c] * zr;
+                    }
+                }
             }
         }
         if (active) {

@@ -9,6 +9,7 @@
 #include "kernels.cuh"
 #include "layout.hpp"
 #include "tile_kernels.cuh"
+#include "extra_kernels.cuh"
 
 #include <nccl.h>
 
@@ -183,6 +184,15 @@ struct opmb200_solver {
     bool register_host = true;
     std::vector<std::pair<const void*, size_t>> registered;
 
+    // standard wells kept outside the matrix (opmb200_set_wells): operator = A - C^T D^-1 B
+    int n_wells = 0, well_dw = 0;
+    std::vector<int32_t> well_ptr_h, well_cells_h; // the structure the device tables were built for
+    DevBuf<int> w_ptr, w_pos, w_head, w_rptr, w_rperf, w_rwell;
+    DevBuf<double> w_B, w_C, w_Dinv, w_z;
+    // CPR helpers (opmb200_cpr_*): staging of caller-side weights / coarse values when they are host pointers
+    DevBuf<double> cpr_w, cpr_coarse;
+    DevBuf<int> cpr_flag;
+
     double t_analysis_s = 0, t_update_ms = 0, t_solve_ms = 0;
     int64_t launches = 0;
     std::vector<double> last_hist;
@@ -327,8 +337,36 @@ int launch_spmv(opmb200_solver* s, const double* x, double* y, bool scaleadd, do
     a.hist = s->hist.p;
     a.dot_out = s->dot_out.p;
     a.check_done = check_done;
+    const bool wells = s->n_wells > 0;
+    a.well_head = wells ? s->w_head.p : nullptr;
+    a.well_ptr = s->w_rptr.p;
+    a.well_perf = s->w_rperf.p;
+    a.well_of = s->w_rwell.p;
+    a.well_C = s->w_C.p;
+    a.well_z = s->w_z.p;
+    a.well_dw = s->well_dw;
     const int grid = s->slice_grid();
-#define SPMV_LAUNCH(SA, ND) spmv_kernel<B, SA, ND><<<grid, kCtaThreads, 0, s->stream>>>(a)
+    if (wells) { // z_w = D_w^-1 B_w x first; the perforated rows of the SpMV subtract C^T z_w
+        WellZArgs z;
+        z.n_wells = s->n_wells;
+        z.dw = s->well_dw;
+        z.wptr = s->w_ptr.p;
+        z.wpos = s->w_pos.p;
+        z.B = s->w_B.p;
+        z.Dinv = s->w_Dinv.p;
+        z.x = x;
+        z.n = s->L.n;
+        z.z = s->w_z.p;
+        z.sc = s->sc.p;
+        z.check_done = check_done;
+        DISPATCH_B(s->b, (well_z_kernel<B><<<(s->n_wells + kWarpsPerCta - 1) / kWarpsPerCta, kCtaThreads, 0, s->stream>>>(z)));
+        TRY(check_launch(s, "well_z"));
+    }
+#define SPMV_LAUNCH(SA, ND)                                                                                            \
+    do {                                                                                                               \
+        if (wells) spmv_kernel<B, SA, ND, true><<<grid, kCtaThreads, 0, s->stream>>>(a);                              \
+        else spmv_kernel<B, SA, ND, false><<<grid, kCtaThreads, 0, s->stream>>>(a);                                   \
+    } while (0)
     DISPATCH_B(s->b, {
         if (scaleadd) {
             if (ndot == 0) SPMV_LAUNCH(true, 0);
@@ -1687,6 +1725,234 @@ int opmb200_timer_stop(opmb200_solver* s, double* elapsed_ms)
     float ms = 0;
     CUDA_TRY(cudaEventElapsedTime(&ms, s->ev_t0, s->ev_t1));
     *elapsed_ms = ms;
+    return OPMB200_SUCCESS;
+}
+
+// ---- standard wells outside the matrix ------------------------------------------------------------
+int opmb200_set_wells(opmb200_solver* s, int n_wells, int dim_wells, const int32_t* well_ptr, const int32_t* cells,
+                      const double* B, const double* C, const double* Dinv)
+{
+    if (!s)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    auto drop_graph = [&]() { // the captured iteration holds the SpMV's arguments by value
+        if (s->iter_graph) {
+            cudaGraphExecDestroy(s->iter_graph);
+            s->iter_graph = nullptr;
+        }
+    };
+    if (n_wells <= 0) {
+        if (s->n_wells != 0)
+            drop_graph();
+        s->n_wells = 0;
+        return OPMB200_SUCCESS;
+    }
+    if (!well_ptr || !cells || !B || !C || !Dinv)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (dim_wells < 1 || dim_wells > kMaxWellEq)
+        return fail(OPMB200_INVALID_ARGUMENT, "dim_wells must be 1.." + std::to_string(kMaxWellEq));
+    if (is_device_ptr(B) || is_device_ptr(C) || is_device_ptr(Dinv))
+        return fail(OPMB200_INVALID_ARGUMENT, "well blocks are host arrays (StandardWellEquations lives on the host)");
+    const int n_perf = well_ptr[n_wells];
+    if (well_ptr[0] != 0 || n_perf < 0)
+        return fail(OPMB200_INVALID_ARGUMENT, "well_ptr must start at 0 and be non-decreasing");
+    for (int w = 0; w < n_wells; ++w)
+        if (well_ptr[w + 1] < well_ptr[w])
+            return fail(OPMB200_INVALID_ARGUMENT, "well_ptr must start at 0 and be non-decreasing");
+    for (int p = 0; p < n_perf; ++p)
+        if (cells[p] < 0 || cells[p] >= s->L.n)
+            return fail(OPMB200_INVALID_ARGUMENT, "perforated cell out of range");
+    const int b = s->b, dw = dim_wells;
+    cudaStream_t st = s->stream;
+    const bool same = s->n_wells == n_wells && s->well_dw == dw && (int)s->well_ptr_h.size() == n_wells + 1
+        && std::equal(well_ptr, well_ptr + n_wells + 1, s->well_ptr_h.begin()) && (int)s->well_cells_h.size() == n_perf
+        && std::equal(cells, cells + n_perf, s->well_cells_h.begin());
+    if (!same) {
+        drop_graph();
+        s->well_ptr_h.assign(well_ptr, well_ptr + n_wells + 1);
+        s->well_cells_h.assign(cells, cells + n_perf);
+        // per perforated row: its perforations in the order the reference's wells visit them (well, perforation)
+        std::vector<int32_t> pos(n_perf), order(n_perf), well_of(n_perf);
+        for (int w = 0; w < n_wells; ++w)
+            for (int p = well_ptr[w]; p < well_ptr[w + 1]; ++p) {
+                pos[p] = s->L.n2r[cells[p]];
+                well_of[p] = w;
+                order[p] = p;
+            }
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return pos[x] < pos[y]; });
+        std::vector<int32_t> head((size_t)s->L.n, -1), rptr(1, 0), rperf(n_perf), rwell(n_perf);
+        for (int k = 0; k < n_perf; ++k) {
+            const int p = order[k];
+            if (k == 0 || pos[p] != pos[order[k - 1]]) {
+                head[pos[p]] = (int32_t)rptr.size() - 1;
+                rptr.push_back(rptr.back());
+            }
+            rperf[k] = p;
+            rwell[k] = well_of[p];
+            ++rptr.back();
+        }
+        CUDA_TRY(s->w_ptr.upload(s->well_ptr_h, st));
+        CUDA_TRY(s->w_pos.upload(pos, st));
+        CUDA_TRY(s->w_head.upload(head, st));
+        CUDA_TRY(s->w_rptr.upload(rptr, st));
+        CUDA_TRY(s->w_rperf.upload(rperf, st));
+        CUDA_TRY(s->w_rwell.upload(rwell, st));
+        CUDA_TRY(s->w_B.alloc((size_t)n_perf * dw * b));
+        CUDA_TRY(s->w_C.alloc((size_t)n_perf * dw * b));
+        CUDA_TRY(s->w_Dinv.alloc((size_t)n_wells * dw * dw));
+        CUDA_TRY(s->w_z.alloc((size_t)n_wells * dw));
+        CUDA_TRY(cudaStreamSynchronize(st)); // the uploads read host vectors that die with this scope
+    }
+    CUDA_TRY(cudaMemcpyAsync(s->w_B.p, B, (size_t)n_perf * dw * b * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->w_C.p, C, (size_t)n_perf * dw * b * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->w_Dinv.p, Dinv, (size_t)n_wells * dw * dw * sizeof(double), cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    s->n_wells = n_wells;
+    s->well_dw = dw;
+    return OPMB200_SUCCESS;
+}
+
+// ---- CPR pieces around the smoother ---------------------------------------------------------------
+namespace {
+// caller vector (host or device) of `count` doubles -> device pointer (staged through `tmp` when it is a host pointer)
+int cpr_in(opmb200_solver* s, const double* user, size_t count, DevBuf<double>& tmp, const double** dev)
+{
+    if (is_device_ptr(user)) {
+        *dev = user;
+        return OPMB200_SUCCESS;
+    }
+    if (tmp.n < count)
+        CUDA_TRY(tmp.alloc(count));
+    CUDA_TRY(cudaMemcpyAsync(tmp.p, user, count * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    *dev = tmp.p;
+    return OPMB200_SUCCESS;
+}
+int cpr_check(opmb200_solver* s, int pressure_index, bool need_values)
+{
+    if (!s)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    if (pressure_index < 0 || pressure_index >= s->b)
+        return fail(OPMB200_INVALID_ARGUMENT, "pressure index out of range");
+    if (need_values && !s->prepared)
+        return fail(OPMB200_NOT_PREPARED, "update_values has not been called");
+    return OPMB200_SUCCESS;
+}
+} // namespace
+
+int opmb200_cpr_quasi_impes_weights(opmb200_solver* s, int pressure_index, int transpose, double* weights)
+{
+    TRY(cpr_check(s, pressure_index, true));
+    if (!weights)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    const size_t len = (size_t)s->len();
+    const bool dev = is_device_ptr(weights);
+    if (!dev && s->cpr_w.n < len)
+        CUDA_TRY(s->cpr_w.alloc(len));
+    if (!s->cpr_flag.p) {
+        CUDA_TRY(s->cpr_flag.alloc(1));
+    }
+    CUDA_TRY(cudaMemsetAsync(s->cpr_flag.p, 0, sizeof(int), s->stream));
+    double* out = dev ? weights : s->cpr_w.p;
+    const int grid = s->slice_grid();
+    DISPATCH_B(s->b, {
+        if (transpose) cpr_weights_kernel<B, true><<<grid, kCtaThreads, 0, s->stream>>>(s->L.n_slices, s->slices.p, s->A.p, s->r2n.p, pressure_index, out, s->cpr_flag.p);
+        else cpr_weights_kernel<B, false><<<grid, kCtaThreads, 0, s->stream>>>(s->L.n_slices, s->slices.p, s->A.p, s->r2n.p, pressure_index, out, s->cpr_flag.p);
+    });
+    TRY(check_launch(s, "cpr_weights"));
+    if (!dev)
+        CUDA_TRY(cudaMemcpyAsync(weights, out, len * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    int* h_bad = reinterpret_cast<int*>(s->h_small);
+    CUDA_TRY(cudaMemcpyAsync(h_bad, s->cpr_flag.p, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (*h_bad)
+        return fail(OPMB200_MATRIX_BLOCK_ERROR, "Singular matrix block");
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_cpr_coarse_entries(opmb200_solver* s, const double* weights, int pressure_index, int transpose,
+                               double* coarse_values)
+{
+    TRY(cpr_check(s, pressure_index, true));
+    if (!weights || !coarse_values)
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    const double* w = nullptr;
+    TRY(cpr_in(s, weights, (size_t)s->len(), s->cpr_w, &w));
+    const size_t nnzb = (size_t)s->L.nnzb;
+    const bool dev = is_device_ptr(coarse_values);
+    if (!dev && s->cpr_coarse.n < nnzb)
+        CUDA_TRY(s->cpr_coarse.alloc(nnzb));
+    double* out = dev ? coarse_values : s->cpr_coarse.p;
+    CUDA_TRY(cudaMemsetAsync(out, 0, nnzb * sizeof(double), s->stream)); // blocks of ghost rows are not stored: 0
+    const int grid = s->slice_grid();
+    DISPATCH_B(s->b, {
+        if (transpose) cpr_coarse_kernel<B, true><<<grid, kCtaThreads, 0, s->stream>>>(s->L.n_slices, s->slices.p, s->slot_col.p, s->slot_src.p, s->A.p, s->r2n.p, w, pressure_index, out);
+        else cpr_coarse_kernel<B, false><<<grid, kCtaThreads, 0, s->stream>>>(s->L.n_slices, s->slices.p, s->slot_col.p, s->slot_src.p, s->A.p, s->r2n.p, w, pressure_index, out);
+    });
+    TRY(check_launch(s, "cpr_coarse"));
+    if (!dev)
+        CUDA_TRY(cudaMemcpyAsync(coarse_values, out, nnzb * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_cpr_restrict(opmb200_solver* s, const double* weights, int pressure_index, int transpose, const double* fine,
+                         double* coarse)
+{
+    TRY(cpr_check(s, pressure_index, false));
+    if (!fine || !coarse || (!transpose && !weights))
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    const size_t len = (size_t)s->len();
+    const double *w = nullptr, *f = nullptr;
+    if (!transpose)
+        TRY(cpr_in(s, weights, len, s->cpr_w, &w));
+    if (is_device_ptr(fine)) {
+        f = fine;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(s->nat0.p, fine, len * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        f = s->nat0.p;
+    }
+    const bool dev = is_device_ptr(coarse);
+    double* out = dev ? coarse : s->nat1.p;
+    DISPATCH_B(s->b, {
+        if (transpose) cpr_restrict_kernel<B, true><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, f, w, pressure_index, out);
+        else cpr_restrict_kernel<B, false><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, f, w, pressure_index, out);
+    });
+    TRY(check_launch(s, "cpr_restrict"));
+    if (!dev)
+        CUDA_TRY(cudaMemcpyAsync(coarse, out, (size_t)s->L.n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return OPMB200_SUCCESS;
+}
+
+int opmb200_cpr_prolongate(opmb200_solver* s, const double* weights, int pressure_index, int transpose,
+                           const double* coarse, double* fine)
+{
+    TRY(cpr_check(s, pressure_index, false));
+    if (!fine || !coarse || (transpose && !weights))
+        return fail(OPMB200_INVALID_ARGUMENT, "null argument");
+    const size_t len = (size_t)s->len();
+    const double *w = nullptr, *c = nullptr;
+    if (transpose)
+        TRY(cpr_in(s, weights, len, s->cpr_w, &w));
+    if (is_device_ptr(coarse)) {
+        c = coarse;
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(s->nat1.p, coarse, (size_t)s->L.n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        c = s->nat1.p;
+    }
+    const bool dev = is_device_ptr(fine);
+    double* out = fine;
+    if (!dev) { // only the pressure component is written when transpose == false: the rest of `fine` is kept
+        CUDA_TRY(cudaMemcpyAsync(s->nat0.p, fine, len * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        out = s->nat0.p;
+    }
+    DISPATCH_B(s->b, {
+        if (transpose) cpr_prolongate_kernel<B, true><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, c, w, pressure_index, out);
+        else cpr_prolongate_kernel<B, false><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, c, w, pressure_index, out);
+    });
+    TRY(check_launch(s, "cpr_prolongate"));
+    if (!dev)
+        CUDA_TRY(cudaMemcpyAsync(fine, out, len * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
     return OPMB200_SUCCESS;
 }
 

@@ -158,6 +158,72 @@ class MatrixAdapter:
         _lib.check(_lib.lib().opmb200_op_applyscaleadd(self._need()._h, float(alpha), _lib.ptr(x), _lib.ptr(y)))
 
 
+class WellModelMatrixAdapter(MatrixAdapter):
+    """Opm::WellModelMatrixAdapter / WellModelGhostLastMatrixAdapter (WellOperators.hpp:224-287, 300-360): the matrix
+    plus the wells as a LinearOperatorExtra.  `wells` = dict(ptr, cells, B, C, Dinv) (see opmb200_set_wells); apply and
+    applyscaleadd -- and every operator application inside FlexibleSolver.apply -- compute (A - C^T D^-1 B) x on the
+    device.  getmat() is still A, so the preconditioner is A's, as in Flow."""
+
+    def __init__(self, matrix: BCSR, wells: dict, interior_size=None, comm=None, halo=None):
+        super().__init__(matrix, interior_size, comm, halo)
+        self.wells = wells
+
+    def _attach(self):
+        self.set_wells(self.wells)
+
+    def set_wells(self, wells: dict | None):
+        """BlackoilWellModel assembles new well equations every Newton iteration"""
+        self.wells = wells
+        h = self._need()._h
+        if not wells or len(wells["ptr"]) <= 1:
+            _lib.check(_lib.lib().opmb200_set_wells(h, 0, 0, None, None, None, None, None))
+            return
+        ptr = np.ascontiguousarray(wells["ptr"], np.int32)
+        cells = np.ascontiguousarray(wells["cells"], np.int32)
+        Bm, Cm, Di = (np.ascontiguousarray(wells[k], np.float64) for k in ("B", "C", "Dinv"))
+        self._keep = (ptr, cells, Bm, Cm, Di)
+        _lib.check(_lib.lib().opmb200_set_wells(h, len(ptr) - 1, int(Di.shape[-1]), ptr.ctypes.data, cells.ctypes.data,
+                                                Bm.ctypes.data, Cm.ctypes.data, Di.ctypes.data))
+
+    def getNumberOfExtraEquations(self) -> int:
+        return 0 if not self.wells else len(self.wells["ptr"]) - 1
+
+
+class PressureTransferPolicy:
+    """The device pieces of Opm::PressureTransferPolicy / Amg::getQuasiImpesWeights around the ILU0/DILU smoother
+    (PressureTransferPolicy.hpp:100-162, getQuasiImpesWeights.hpp:64-111; GPU twin gpuistl/detail/
+    cpr_amg_operations.cu:35-178).  All vectors natural order, numpy or torch (host or device)."""
+
+    def __init__(self, solver: "FlexibleSolver", pressure_var_index: int = 0, transpose: bool = False, weights=None):
+        self.solver, self.p, self.transpose = solver, int(pressure_var_index), bool(transpose)
+        self.weights = weights
+
+    def quasi_impes_weights(self, out=None):
+        A = self.solver.op.getmat()
+        w = np.zeros(A.n * A.b) if out is None else out
+        _lib.check(_lib.lib().opmb200_cpr_quasi_impes_weights(self.solver._h, self.p, int(self.transpose), _lib.ptr(w)))
+        self.weights = w
+        return w
+
+    def calculateCoarseEntries(self, out=None):
+        A = self.solver.op.getmat()
+        c = np.zeros(A.nnzb) if out is None else out
+        _lib.check(_lib.lib().opmb200_cpr_coarse_entries(self.solver._h, _lib.ptr(self.weights), self.p,
+                                                         int(self.transpose), _lib.ptr(c)))
+        return c
+
+    def moveToCoarseLevel(self, fine, out=None):
+        c = np.zeros(self.solver.op.getmat().n) if out is None else out
+        _lib.check(_lib.lib().opmb200_cpr_restrict(self.solver._h, _lib.ptr(self.weights), self.p, int(self.transpose),
+                                                   _lib.ptr(fine), _lib.ptr(c)))
+        return c
+
+    def moveToFineLevel(self, coarse, fine):
+        _lib.check(_lib.lib().opmb200_cpr_prolongate(self.solver._h, _lib.ptr(self.weights), self.p, int(self.transpose),
+                                                     _lib.ptr(coarse), _lib.ptr(fine)))
+        return fine
+
+
 class PreconditionerWithUpdate:
     """Dune::PreconditionerWithUpdate<X,Y>: pre/apply/post/update/hasPerfectUpdate"""
 
@@ -253,6 +319,8 @@ class FlexibleSolver:
                                              C.byref(halo_struct) if halo_struct else None, C.byref(self._h)))
         op._solver = self
         self.update()
+        if hasattr(op, "_attach"):
+            op._attach()
 
     # ---- Dune::InverseOperator ------------------------------------------------------------------
     def apply(self, x, rhs, reduction: float | None = None) -> InverseOperatorResult:

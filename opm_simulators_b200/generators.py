@@ -207,3 +207,44 @@ def laplace_like(n_side: int, b: int, rng, dims: int = 2, asym: float = 0.0) -> 
     if asym:
         blks[~isdiag & (rows < cols)] *= (1.0 + asym)
     return BCSR.from_block_coo(n, rows, cols, blks)
+
+
+def standard_wells(A: BCSR, n_wells: int = 8, perfs: int = 12, dim_wells: int | None = None, seed: int = 7,
+                   strength: float = 0.02, shared_cells: int = 0):
+    """Synthetic StandardWell equations for the operator A - sum_w C_w^T D_w^-1 B_w
+    (wells/StandardWellEquations.hpp: duneB_, duneC_ with one dim_wells x b block per perforation, invDuneD_).
+
+    Every well perforates `perfs` cells of a vertical-ish line of rows (stride = a random step), wells may share
+    `shared_cells` cells (two wells perforating one cell, which the reference allows).  The blocks are scaled by
+    `strength` relative to the perforated cell's diagonal block so that A - C^T D^-1 B stays well conditioned.
+    Returns dict(ptr, cells, B, C, Dinv) in the layout of include/opmb200.h (opmb200_set_wells)."""
+    rng = np.random.default_rng(seed)
+    b = A.b
+    dw = b + 1 if dim_wells is None else dim_wells  # numWellEq = numEq + 1 for the black-oil StandardWell
+    n = A.n
+    ptr, cells = [0], []
+    for w in range(n_wells):
+        start = int(rng.integers(0, max(1, n - 1)))
+        step = int(rng.integers(1, max(2, n // (4 * perfs) + 2)))
+        c = [(start + k * step) % n for k in range(perfs if w % 3 else max(1, perfs // 2))]
+        c = list(dict.fromkeys(c))  # a well perforates a cell once
+        if shared_cells and w > 0 and cells:
+            for extra in cells[:shared_cells]:
+                if extra not in c:
+                    c.append(extra)
+        cells += c
+        ptr.append(len(cells))
+    cells = np.asarray(cells, np.int32)
+    n_perf = len(cells)
+    diag = np.empty((n_perf,))
+    for k, cell in enumerate(cells):
+        row = slice(A.rowptr[cell], A.rowptr[cell + 1])
+        d = row.start + int(np.searchsorted(A.col[row], cell))
+        diag[k] = np.abs(A.val[d]).max()
+    scale = np.sqrt(strength * diag)[:, None, None]
+    Bm = rng.uniform(-1.0, 1.0, (n_perf, dw, b)) * scale
+    Cm = rng.uniform(-1.0, 1.0, (n_perf, dw, b)) * scale
+    D = rng.uniform(-0.3, 0.3, (n_wells, dw, dw)) + np.eye(dw) * 2.0
+    Dinv = np.linalg.inv(D)
+    return dict(ptr=np.asarray(ptr, np.int32), cells=cells, B=np.ascontiguousarray(Bm), C=np.ascontiguousarray(Cm),
+                Dinv=np.ascontiguousarray(Dinv))

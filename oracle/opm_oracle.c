@@ -492,6 +492,11 @@ typedef struct {
     const double* val;
     double* dinv;
     double* lu;
+    /* standard wells kept outside the matrix (matrix-add-well-contributions=false); borrowed arrays */
+    int nw, dw;
+    const int *wptr, *wcells;
+    const double *wB, *wC, *wDinv;
+    double* wscratch; /* scaleAddRes_ of WellModelAsLinearOperator */
 } orc_sub;
 
 struct orc_par {
@@ -523,6 +528,7 @@ void orc_par_destroy(orc_par* h)
     for (int p = 0; p < h->nsub; ++p) {
         free(h->sub[p].dinv);
         free(h->sub[p].lu);
+        free(h->sub[p].wscratch);
     }
     free(h->sub);
     free(h->gscratch);
@@ -542,6 +548,87 @@ int orc_par_set_sub(orc_par* h, int p, int n, int interior, const int* rowptr, c
     s->val = val;
     s->l2g = l2g;
     return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Standard wells as a linear operator: y -= C^T (D^-1 (B x)), well after well
+ * (WellOperators.hpp:84-91 apply, :144-164 applySingleWell; StandardWellEquations.cpp:132-148:
+ * Bx = B.mv(x), invDBx = invD.mv(Bx), Ax -= C.mmtv(invDBx)).  Perforation p of well w touches
+ * cell cells[p]; B and C hold one dw x b block (row-major) per perforation, Dinv one dw x dw
+ * block per well.  The running sums follow Dune's mv / mmtv loop order.
+ * ---------------------------------------------------------------------------------------- */
+void orc_well_apply(int nw, int dw, int b, const int* wptr, const int* cells, const double* B, const double* C,
+                    const double* Dinv, const double* x, double* y)
+{
+    double z1[16], z2[16];
+    for (int w = 0; w < nw; ++w) {
+        for (int r = 0; r < dw; ++r)
+            z1[r] = 0.0;
+        for (int p = wptr[w]; p < wptr[w + 1]; ++p) { /* BCRSMatrix::mv: block.umv per entry */
+            const double* Bp = B + (size_t)p * dw * b;
+            const double* xc = x + (size_t)cells[p] * b;
+            for (int r = 0; r < dw; ++r)
+                for (int c = 0; c < b; ++c)
+                    z1[r] += Bp[r * b + c] * xc[c];
+        }
+        const double* Dw = Dinv + (size_t)w * dw * dw;
+        for (int r = 0; r < dw; ++r) {
+            z2[r] = 0.0;
+            for (int c = 0; c < dw; ++c)
+                z2[r] += Dw[r * dw + c] * z1[c];
+        }
+        for (int p = wptr[w]; p < wptr[w + 1]; ++p) { /* BCRSMatrix::mmtv: y[j] -= A[i][j]^T x[i] */
+            const double* Cp = C + (size_t)p * dw * b;
+            double* yc = y + (size_t)cells[p] * b;
+            for (int r = 0; r < dw; ++r)
+                for (int c = 0; c < b; ++c)
+                    yc[c] -= Cp[r * b + c] * z2[r];
+        }
+    }
+}
+
+int orc_par_set_wells(orc_par* h, int p, int nw, int dw, const int* wptr, const int* cells, const double* B,
+                      const double* C, const double* Dinv)
+{
+    if (p < 0 || p >= h->nsub || nw < 0 || dw < 0 || dw > 16)
+        return ORC_ERR_ARG;
+    orc_sub* s = &h->sub[p];
+    s->nw = nw;
+    s->dw = dw;
+    s->wptr = wptr;
+    s->wcells = cells;
+    s->wB = B;
+    s->wC = C;
+    s->wDinv = Dinv;
+    return ORC_OK;
+}
+
+/* WellModelMatrixAdapter / WellModelGhostLastMatrixAdapter::apply tail (WellOperators.hpp:244-250, 336-339):
+ * wellOper.apply(x, y) then ghostLastProject(y) */
+static void sub_well_apply(const orc_sub* s, int b, const double* x, double* y)
+{
+    if (s->nw <= 0)
+        return;
+    orc_well_apply(s->nw, s->dw, b, s->wptr, s->wcells, s->wB, s->wC, s->wDinv, x, y);
+    for (size_t k = (size_t)s->interior * b; k < (size_t)s->n * b; ++k)
+        y[k] = 0.0;
+}
+/* WellModelAsLinearOperator::applyscaleadd (WellOperators.hpp:93-109): scaleAddRes = 0; apply(x, scaleAddRes);
+ * y.axpy(alpha, scaleAddRes); then ghostLastProject(y) (:353-355) */
+static void sub_well_applyscaleadd(orc_sub* s, int b, double alpha, const double* x, double* y)
+{
+    if (s->nw <= 0)
+        return;
+    const size_t len = (size_t)s->n * b;
+    if (!s->wscratch)
+        s->wscratch = (double*)malloc(len * sizeof(double));
+    for (size_t k = 0; k < len; ++k)
+        s->wscratch[k] = 0.0;
+    orc_well_apply(s->nw, s->dw, b, s->wptr, s->wcells, s->wB, s->wC, s->wDinv, x, s->wscratch);
+    for (size_t k = 0; k < len; ++k)
+        y[k] += alpha * s->wscratch[k];
+    for (size_t k = (size_t)s->interior * b; k < len; ++k)
+        y[k] = 0.0;
 }
 
 const double* orc_par_dinv(orc_par* h, int p) { return h->sub[p].dinv; }
@@ -697,6 +784,7 @@ static void op_apply(orc_par* h, int repeats, double** x, double** y, double** t
         for (int p = 0; p < h->nsub; ++p) {
             const orc_sub* s = &h->sub[p];
             orc_spmv(s->n, b, s->rowptr, s->col, s->val, s->interior, x[p], y[p]);
+            sub_well_apply(s, b, x[p], y[p]);
         }
         return;
     }
@@ -705,6 +793,7 @@ static void op_apply(orc_par* h, int repeats, double** x, double** y, double** t
         for (int p = 0; p < h->nsub; ++p) {
             const orc_sub* s = &h->sub[p];
             orc_spmv(s->n, b, s->rowptr, s->col, s->val, s->interior, t1[p], y[p]);
+            sub_well_apply(s, b, t1[p], y[p]);
         }
         vec_copy(h, t1, y);
     }
@@ -717,8 +806,9 @@ static void op_applyscaleadd(orc_par* h, int repeats, double alpha, double** x, 
     if (repeats <= 1) {
 #pragma omp parallel for schedule(static)
         for (int p = 0; p < h->nsub; ++p) {
-            const orc_sub* s = &h->sub[p];
+            orc_sub* s = &h->sub[p];
             orc_spmv_scaleadd(s->n, b, s->rowptr, s->col, s->val, s->interior, alpha, x[p], y[p]);
+            sub_well_applyscaleadd(s, b, alpha, x[p], y[p]);
         }
         return;
     }

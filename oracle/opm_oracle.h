@@ -64,6 +64,12 @@ void orc_spmv(int n, int b, const int* rowptr, const int* col, const double* val
 void orc_spmv_scaleadd(int n, int b, const int* rowptr, const int* col, const double* val, int interior,
                        double alpha, const double* x, double* y);
 
+/* WellOperators.hpp:84-91,144-164 + StandardWellEquations.cpp:132-148: y -= C^T (Dinv (B x)) well after well.
+ * wptr[nw+1] perforation ranges, cells[nperf] perforated cell of each perforation, B/C [nperf][dw][b],
+ * Dinv [nw][dw][dw], all row-major */
+void orc_well_apply(int nw, int dw, int b, const int* wptr, const int* cells, const double* B, const double* C,
+                    const double* Dinv, const double* x, double* y);
+
 /* ISTLSolver.cpp:56-75 */
 void orc_make_overlap_rows_invalid(int n, int b, const int* rowptr, const int* col, double* val, int interior);
 
@@ -85,6 +91,10 @@ void orc_par_destroy(orc_par* h);
 /* l2g may be NULL for a serial system (nsub == 1).  Arrays are borrowed, not copied. */
 int orc_par_set_sub(orc_par* h, int p, int n, int interior, const int* rowptr, const int* col,
                     const double* val, const int* l2g);
+/* wells of subdomain p stay outside the matrix (WellModelMatrixAdapter, WellOperators.hpp:224-287): every
+ * op.apply / applyscaleadd of the solver adds the well operator.  Arrays are borrowed.  nw = 0 removes them. */
+int orc_par_set_wells(orc_par* h, int p, int nw, int dw, const int* wptr, const int* cells, const double* B,
+                      const double* C, const double* Dinv);
 /* builds the preconditioner on every subdomain; kind = ORC_PREC_*; w = ILU0 relaxation */
 int orc_par_prec_update(orc_par* h, int kind, double w);
 /* Dune::BlockPreconditioner::apply: local apply, copyOwnerToAll, (ILU0: relaxation) */

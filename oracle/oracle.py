@@ -92,6 +92,9 @@ def lib():
         L.orc_par_dinv.restype = C.POINTER(C.c_double)
         L.orc_par_lu.argtypes = [C.c_void_p, C.c_int]
         L.orc_par_lu.restype = C.POINTER(C.c_double)
+        L.orc_well_apply.argtypes = [C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p, _f64p, _f64p]
+        L.orc_par_set_wells.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, _i32p, _f64p, _f64p, _f64p]
+        L.orc_par_set_wells.restype = C.c_int
         _lib = L
     return _lib
 
@@ -174,6 +177,16 @@ def spmv_scaleadd(rowptr, col, val, alpha, x, y, interior=None):
     y = _f64(y).reshape(-1).copy()
     lib().orc_spmv_scaleadd(n, b, rowptr, col, val.reshape(-1), n if interior is None else interior,
                             alpha, x.reshape(-1), y)
+    return y
+
+
+def well_apply(wells, x, y, b):
+    """y -= C^T (Dinv (B x)) well after well (WellOperators.hpp:84-91, StandardWellEquations.cpp:132-148); returns y"""
+    wp, wc = _i32(wells["ptr"]), _i32(wells["cells"])
+    B, Cm, Di = _f64(wells["B"]), _f64(wells["C"]), _f64(wells["Dinv"])
+    y = _f64(y).reshape(-1).copy()
+    lib().orc_well_apply(len(wp) - 1, int(Di.shape[-1]), b, wp, wc, B.reshape(-1), Cm.reshape(-1), Di.reshape(-1),
+                         _f64(x).reshape(-1), y)
     return y
 
 
@@ -269,6 +282,18 @@ class ParSystem:
             assert v.dtype == np.float64 and v.flags.c_contiguous
             arr[p] = v.ctypes.data_as(C.POINTER(C.c_double))
         return arr
+
+    def set_wells(self, wells, p=0):
+        """wells: dict(ptr[nw+1], cells[nperf], B[nperf,dw,b], C[nperf,dw,b], Dinv[nw,dw,dw]) kept OUTSIDE the matrix
+        (WellModelMatrixAdapter): every operator application of bicgstab() adds y -= C^T Dinv B x"""
+        wp, wc = _i32(wells["ptr"]), _i32(wells["cells"])
+        B, Cm, Di = _f64(wells["B"]), _f64(wells["C"]), _f64(wells["Dinv"])
+        self._wells = getattr(self, "_wells", {})
+        self._wells[p] = (wp, wc, B, Cm, Di)  # keep alive
+        rc = lib().orc_par_set_wells(self.h, p, len(wp) - 1, int(Di.shape[-1]), wp, wc, B.reshape(-1), Cm.reshape(-1),
+                                     Di.reshape(-1))
+        if rc:
+            raise OracleError(rc)
 
     def prec_update(self, kind, relaxation=1.0):
         if isinstance(kind, str):
@@ -429,3 +454,62 @@ class RefMixedSolver:
             R.bsr_free(self.A)
         except Exception:
             pass
+
+
+# --------------------------------------------------------------------------------------------
+# CPR pieces around the smoother (numpy restatements; test infrastructure like everything here)
+# --------------------------------------------------------------------------------------------
+def _diag_index(rowptr, col):
+    n = len(rowptr) - 1
+    d = np.empty(n, np.int64)
+    for i in range(n):
+        k = rowptr[i] + np.searchsorted(col[rowptr[i]:rowptr[i + 1]], i)
+        assert col[k] == i
+        d[i] = k
+    return d
+
+
+def quasi_impes_weights(rowptr, col, val, pressure_index, transpose=False):
+    """Amg::getQuasiImpesWeights (getQuasiImpesWeights.hpp:64-111): per row solve D^T w = e_p (transpose: D w = e_p)
+    with the diagonal block D, then w /= max|w|.  -> [n, b]"""
+    val = _f64(val)
+    b = val.shape[-1]
+    D = val[_diag_index(rowptr, col)]
+    rhs = np.zeros(b)
+    rhs[pressure_index] = 1.0
+    M = D if transpose else np.transpose(D, (0, 2, 1))
+    w = np.linalg.solve(M, np.broadcast_to(rhs, (len(D), b))[..., None])[..., 0]
+    return w / np.abs(w).max(axis=1, keepdims=True)
+
+
+def cpr_coarse_entries(rowptr, col, val, weights, pressure_index, transpose=False):
+    """PressureTransferPolicy::calculateCoarseEntries (gpuistl/detail/cpr_amg_operations.cu:79-123):
+    transpose False: sum_j A_k[j][p] w_row[j];  True: sum_j A_k[p][j] w_col[j].  -> [nnzb]"""
+    val = _f64(val)
+    w = _f64(weights).reshape(len(rowptr) - 1, -1)
+    rows = np.repeat(np.arange(len(rowptr) - 1), np.diff(rowptr))
+    if transpose:
+        return np.einsum("kj,kj->k", val[:, pressure_index, :], w[np.asarray(col)])
+    return np.einsum("kj,kj->k", val[:, :, pressure_index], w[rows])
+
+
+def cpr_restrict(fine, weights, pressure_index, transpose=False):
+    """PressureTransferPolicy::moveToCoarseLevel (cpr_amg_operations.cu:126-151)"""
+    w = _f64(weights)
+    if w.ndim != 2:
+        raise ValueError("weights must be [n, b]")
+    f = _f64(fine).reshape(-1, w.shape[-1])
+    return f[:, pressure_index].copy() if transpose else np.einsum("ik,ik->i", f, w)
+
+
+def cpr_prolongate(coarse, fine, weights, pressure_index, transpose=False):
+    """PressureTransferPolicy::moveToFineLevel (PressureTransferPolicy.hpp:148-162): returns the updated fine vector"""
+    w = _f64(weights)
+    b = w.shape[-1]
+    f = _f64(fine).reshape(-1, b).copy()
+    c = _f64(coarse).reshape(-1)
+    if transpose:
+        f[:] = c[:, None] * w
+    else:
+        f[:, pressure_index] = c
+    return f.reshape(-1)

@@ -140,6 +140,62 @@ int main(int argc, char** argv)
         CHECK(std::abs(v[i / bz][i % bz] - expected[i]) <= 1e-5 * std::abs(expected[i]));
     prec->update();
 
+    // ---- wells outside the matrix: Solver::setWells, the solution of (A - C^T D^-1 B) x = b satisfies that system ----
+    {
+        prm.put("preconditioner.type", std::string("dilu"));
+        prm.put("tol", 1e-10);
+        Opm::b200::Solver<Operator> solver(op, prm.toJson());
+        Opm::b200::FlatWells w; // one well, two perforations (cells 0 and 2), dimWells = 2
+        w.dimWells = 2;
+        w.cells = {0, 2};
+        w.ptr = {0, 2};
+        for (int p = 0; p < 2; ++p)
+            for (int r = 0; r < 2; ++r)
+                for (int c = 0; c < bz; ++c) {
+                    w.B.push_back(1e-3 * (1 + p + r + c));
+                    w.C.push_back(2e-3 * (1 + p - r + 2 * c));
+                }
+        w.Dinv = {0.5, 0.1, -0.2, 0.4};
+        solver.setWells(w);
+        Vector x(rhs0.size()), rhs = rhs0;
+        for (std::size_t i = 0; i < x.size(); ++i)
+            for (int c = 0; c < bz; ++c)
+                x[i][c] = 0.0;
+        Dune::InverseOperatorResult res;
+        solver.apply(x, rhs, res);
+        CHECK(res.converged);
+        // residual of the combined operator, computed here on the host
+        Vector y(rhs0.size());
+        for (auto row = A->begin(); row != A->end(); ++row) {
+            for (int r = 0; r < bz; ++r)
+                y[row.index()][r] = 0.0;
+            for (auto col = row->begin(); col != row->end(); ++col)
+                for (int r = 0; r < bz; ++r)
+                    for (int c = 0; c < bz; ++c)
+                        y[row.index()][r] += (*col)[r][c] * x[col.index()][c];
+        }
+        double z1[2] = {0, 0}, z2[2];
+        for (int p = 0; p < 2; ++p)
+            for (int r = 0; r < 2; ++r)
+                for (int c = 0; c < bz; ++c)
+                    z1[r] += w.B[(p * 2 + r) * bz + c] * x[w.cells[p]][c];
+        for (int r = 0; r < 2; ++r)
+            z2[r] = w.Dinv[r * 2] * z1[0] + w.Dinv[r * 2 + 1] * z1[1];
+        for (int p = 0; p < 2; ++p)
+            for (int r = 0; r < 2; ++r)
+                for (int c = 0; c < bz; ++c)
+                    y[w.cells[p]][c] -= w.C[(p * 2 + r) * bz + c] * z2[r];
+        double rn = 0, bn = 0;
+        for (std::size_t i = 0; i < y.size(); ++i)
+            for (int c = 0; c < bz; ++c) {
+                rn += (rhs0[i][c] - y[i][c]) * (rhs0[i][c] - y[i][c]);
+                bn += rhs0[i][c] * rhs0[i][c];
+            }
+        CHECK(std::sqrt(rn) <= 1e-8 * std::sqrt(bn));
+        solver.clearWells();
+        std::printf("b200bicgstab + wells: iterations=%d reduction=%.3e OK\n", res.iterations, res.reduction);
+    }
+
     // ---- error contract: unknown type -> std::invalid_argument (:219-227; PreconditionerFactory_impl.hpp:98-106)
     bool thrown = false;
     try {

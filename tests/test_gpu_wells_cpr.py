@@ -1,0 +1,201 @@
+"""GPU parity of the operators either side of the smoother, through the C ABI:
+
+  * standard wells kept outside the matrix: y = (A - C^T D^-1 B) x inside the SpMV (opmb200_set_wells) against the
+    oracle's WellModelAsLinearOperator restatement, stand-alone and inside BiCGSTAB;
+  * the CPR transfer pieces (quasi-IMPES weights, coarse entries, restriction, prolongation) against the numpy
+    restatements, on the fixture of the reference's own test (tests/gpuistl/test_GpuPressureTransferPolicy.cpp:
+    N = 10 block-tridiagonal, U(-10, 10), tolerance 1e-10 percent there, 1e-10 relative here)."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from opm_simulators_b200 import generators
+from opm_simulators_b200.bcsr import BCSR
+from opm_simulators_b200.flexible_solver import (FlexibleSolver, InvalidArgument, MatrixAdapter, PressureTransferPolicy,
+                                                 WellModelMatrixAdapter)
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def opts(prec, schedule, tol=1e-2, maxiter=200):
+    return {"solver": "bicgstab", "tol": tol, "maxiter": maxiter, "preconditioner": {"type": prec},
+            "b200": {"schedule": schedule}}
+
+
+def oracle_op(A, wells, x, y0=None, alpha=None):
+    """WellModelMatrixAdapter::apply / applyscaleadd (WellOperators.hpp:244-262) on the host"""
+    if alpha is None:
+        y = orc.spmv(A.rowptr, A.col, A.val, x)
+        return orc.well_apply(wells, x, y, A.b)
+    y = orc.spmv_scaleadd(A.rowptr, A.col, A.val, alpha, x, y0)
+    extra = orc.well_apply(wells, x, np.zeros_like(x), A.b)  # scaleAddRes_ = -C^T D^-1 B x
+    return y + alpha * extra
+
+
+CASES = [("blackoil_b3", 3, 4, 0), ("blackoil_b3_shared", 3, 4, 3), ("blackoil_b4", 4, 5, 1), ("lap_b2", 2, 3, 0),
+         ("lap_b1", 1, 2, 0)]
+
+
+def make_case(name, b, dw, shared):
+    if name.startswith("blackoil"):
+        A = generators.blackoil_system(9, 8, 7, b=b, seed=21, with_rhs=False)["A"]
+    else:
+        A = generators.laplace_like(12, b, np.random.default_rng(5), dims=2, asym=0.2)
+    wells = generators.standard_wells(A, n_wells=40, perfs=9, dim_wells=dw, seed=4, shared_cells=shared)
+    return A, wells
+
+
+@pytest.mark.parametrize("schedule", ["levels", "tiles"])
+@pytest.mark.parametrize("name,b,dw,shared", CASES)
+def test_well_operator_apply_parity(name, b, dw, shared, schedule):
+    A, wells = make_case(name, b, dw, shared)
+    op = WellModelMatrixAdapter(A, wells)
+    fs = FlexibleSolver(op, opts("dilu", schedule))
+    rng = np.random.default_rng(1)
+    x, y0 = rng.standard_normal(A.n * b), rng.standard_normal(A.n * b)
+    y = np.zeros_like(x)
+    op.apply(x, y)
+    assert rel_err(y, oracle_op(A, wells, x)) < TOL
+    assert rel_err(y, orc.spmv(A.rowptr, A.col, A.val, x)) > 1e-6  # the wells do something
+    y = y0.copy()
+    op.applyscaleadd(-0.7, x, y)
+    assert rel_err(y, oracle_op(A, wells, x, y0, -0.7)) < TOL
+    # new well equations with the same perforations (every Newton iteration), then a different well set, then none
+    wells2 = dict(wells, B=wells["B"] * 1.5, C=wells["C"] * 0.5)
+    op.set_wells(wells2)
+    op.apply(x, y)
+    assert rel_err(y, oracle_op(A, wells2, x)) < TOL
+    wells3 = generators.standard_wells(A, n_wells=3, perfs=5, dim_wells=dw, seed=9)
+    op.set_wells(wells3)
+    op.apply(x, y)
+    assert rel_err(y, oracle_op(A, wells3, x)) < TOL
+    op.set_wells(None)
+    op.apply(x, y)
+    assert rel_err(y, orc.spmv(A.rowptr, A.col, A.val, x)) < TOL
+    fs.close()
+
+
+@pytest.mark.parametrize("schedule", ["levels", "tiles"])
+@pytest.mark.parametrize("prec", ["dilu", "ilu0"])
+@pytest.mark.parametrize("tol", [1e-3, 1e-4])
+def test_bicgstab_with_wells_parity(prec, tol, schedule):
+    s = generators.config("C3", scale=0.2)
+    A = s["A"]
+    # strength 0.02: 3 / 17 iterations with the wells against 1 / 2 without (the wells matter)
+    wells = generators.standard_wells(A, n_wells=12, perfs=20, seed=3, shared_cells=1, strength=0.02)
+    op = WellModelMatrixAdapter(A, wells)
+    fs = FlexibleSolver(op, opts(prec, schedule, tol=tol))
+    ps = orc.ParSystem.serial(A.rowptr, A.col, A.val)
+    ps.set_wells(wells)
+    ps.prec_update(prec)
+    for rep in range(2):  # the second solve replays the captured iteration graph
+        x, r = np.zeros(A.n * 3), s["rhs"].copy()
+        res = fs.apply(x, r)
+        xo, ro, reso, ho = ps.bicgstab([s["rhs"]], tol=tol, maxiter=200)
+        h = fs.history()
+        assert res.converged and reso["converged"]
+        assert abs(res.iterations - reso["iterations"]) <= 1, (res.iterations, reso["iterations"])
+        k = min(len(h), len(ho), 12)
+        assert np.allclose(h[:k], ho[:k], rtol=1e-6)
+        if len(h) == len(ho):
+            assert rel_err(x, xo[0]) < 1e-10, rel_err(x, xo[0])
+        true_r = s["rhs"] - oracle_op(A, wells, x)
+        assert np.linalg.norm(true_r) / np.linalg.norm(s["rhs"]) < tol * 1.01
+    # without the wells the same handle solves A x = b again (graph dropped, operator back to A)
+    op.set_wells(None)
+    x, r = np.zeros(A.n * 3), s["rhs"].copy()
+    res = fs.apply(x, r)
+    xo, reso, ho = orc.solve_serial(A.rowptr, A.col, A.val, s["rhs"], prec=prec, tol=tol)
+    assert abs(res.iterations - reso["iterations"]) <= 1
+    assert np.linalg.norm(s["rhs"] - orc.spmv(A.rowptr, A.col, A.val, x)) / np.linalg.norm(s["rhs"]) < tol * 1.01
+    fs.close()
+
+
+def test_set_wells_argument_checks():
+    A, wells = make_case("blackoil_b3", 3, 4, 0)
+    op = WellModelMatrixAdapter(A, None)
+    fs = FlexibleSolver(op, opts("dilu", "levels"))
+    bad = dict(wells, cells=wells["cells"].copy())
+    bad["cells"][0] = A.n
+    with pytest.raises(InvalidArgument):
+        op.set_wells(bad)
+    bad = dict(wells, Dinv=np.zeros((len(wells["ptr"]) - 1, 9, 9)))
+    with pytest.raises(InvalidArgument):
+        op.set_wells(bad)
+    fs.close()
+
+
+# ---- CPR ---------------------------------------------------------------------------------------------
+def _tridiag_fixture(b, n=10, seed=0):
+    rng = np.random.default_rng(seed)
+    r, c = [], []
+    for i in range(n):
+        for j in (i - 1, i, i + 1):
+            if 0 <= j < n:
+                r.append(i)
+                c.append(j)
+    return BCSR.from_block_coo(n, np.array(r), np.array(c), rng.uniform(-10, 10, (len(r), b, b)))
+
+
+def _cpr_check(A, fs, p, transpose):
+    b = A.b
+    pol = PressureTransferPolicy(fs, p, transpose)
+    w = pol.quasi_impes_weights().reshape(A.n, b)
+    wo = orc.quasi_impes_weights(A.rowptr, A.col, A.val, p, transpose)
+    assert rel_err(w, wo) < TOL
+    coarse = pol.calculateCoarseEntries()
+    assert rel_err(coarse, orc.cpr_coarse_entries(A.rowptr, A.col, A.val, wo, p, transpose)) < TOL
+    rng = np.random.default_rng(7)
+    fine = rng.standard_normal(A.n * b)
+    assert rel_err(pol.moveToCoarseLevel(fine), orc.cpr_restrict(fine, wo, p, transpose)) < TOL
+    lhs = rng.standard_normal(A.n)
+    out = fine.copy()
+    pol.moveToFineLevel(lhs, out)
+    assert rel_err(out, orc.cpr_prolongate(lhs, fine, wo, p, transpose)) < TOL
+
+
+@pytest.mark.parametrize("b", [1, 2, 3, 4])
+@pytest.mark.parametrize("transpose", [False, True])
+def test_cpr_pieces_reference_fixture(b, transpose):
+    """the fixture of tests/gpuistl/test_GpuPressureTransferPolicy.cpp, every pressure index"""
+    A = _tridiag_fixture(b)
+    fs = FlexibleSolver(MatrixAdapter(A), opts("dilu", "levels"))
+    for p in range(b):
+        _cpr_check(A, fs, p, transpose)
+    fs.close()
+
+
+@pytest.mark.parametrize("schedule", ["levels", "tiles"])
+@pytest.mark.parametrize("cfg,scale", [("C3", 0.25), ("C2", 0.4), ("C5", 0.12)])
+def test_cpr_pieces_blackoil(cfg, scale, schedule):
+    A = generators.config(cfg, scale=scale, with_rhs=False)["A"]
+    fs = FlexibleSolver(MatrixAdapter(A), opts("ilu0", schedule))
+    _cpr_check(A, fs, 0, False)
+    _cpr_check(A, fs, 1, True)
+    fs.close()
+
+
+def test_cpr_pieces_device_pointers():
+    torch = pytest.importorskip("torch")
+    A = generators.config("C3", scale=0.2, with_rhs=False)["A"]
+    fs = FlexibleSolver(MatrixAdapter(A), opts("dilu", "tiles"))
+    dev = dict(dtype=torch.float64, device="cuda")
+    w = torch.zeros(A.n * 3, **dev)
+    pol = PressureTransferPolicy(fs, 0, False)
+    pol.quasi_impes_weights(out=w)
+    wo = orc.quasi_impes_weights(A.rowptr, A.col, A.val, 0, False)
+    torch.cuda.synchronize()
+    assert rel_err(w.cpu().numpy(), wo) < TOL
+    coarse = torch.zeros(A.nnzb, **dev)
+    pol.calculateCoarseEntries(out=coarse)
+    assert rel_err(coarse.cpu().numpy(), orc.cpr_coarse_entries(A.rowptr, A.col, A.val, wo, 0, False)) < TOL
+    fine_h = np.random.default_rng(2).standard_normal(A.n * 3)
+    fine = torch.from_numpy(fine_h).cuda()
+    c = torch.zeros(A.n, **dev)
+    pol.moveToCoarseLevel(fine, out=c)
+    assert rel_err(c.cpu().numpy(), orc.cpr_restrict(fine_h, wo, 0, False)) < TOL
+    pol.moveToFineLevel(c, fine)
+    assert rel_err(fine.cpu().numpy(), orc.cpr_prolongate(c.cpu().numpy(), fine_h, wo, 0, False)) < TOL
+    fs.close()
