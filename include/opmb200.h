@@ -162,8 +162,14 @@ int opmb200_comm_destroy(opmb200_comm* comm);
  *    setupPropertyTree.cpp:190-203), or NULL for the defaults.  Keys read: solver ("bicgstab"),
  *    tol (1e-2), maxiter (200), verbosity (0), preconditioner.type ("paroverilu0" | "ilu0" |
  *    "dilu" | the reference's GPU aliases "opmilu0", "opmgpuilu0", "gpudilu"), preconditioner.
- *    relaxation (1.0), preconditioner.ilulevel (0).  Values may be JSON strings or numbers
+ *    relaxation (1.0), preconditioner.ilulevel (0; > 0 is rejected).  The reference's GPU tuning keys
+ *    preconditioner.split_matrix / tune_gpu_kernels / reorder (StandardPreconditioners_gpu_serial.hpp:77-80, 92-96)
+ *    are accepted, type-checked and have no effect (one implementation here); preconditioner.
+ *    mixed_precision_scheme != 0 is rejected (fp64 storage only).  Values may be JSON strings or numbers
  *    (boost::property_tree stores strings).
+ * Stream ordering: every call works on the handle's own stream and returns after that stream has drained.  A
+ *    DEVICE pointer argument (values, x, b, ...) must be complete when the call is made -- the library does not
+ *    order itself behind the stream that produced it (synchronise that stream, or its event, first).
  * n_interior: number of owner rows (== n_rows when serial); rows >= n_interior are ghosts.
  * comm, halo: NULL when serial. */
 int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int64_t nnzb,

@@ -647,6 +647,14 @@ int parse_options(opmb200_solver* s, const char* json)
             return fail(OPMB200_BAD_OPTIONS, "preconditioner.ilulevel > 0 (ILU(n)) is outside this path");
         if (prm.get<int>("preconditioner.mixed_precision_scheme", 0) != 0)
             return fail(OPMB200_BAD_OPTIONS, "preconditioner.mixed_precision_scheme != 0 is outside this path");
+        // tuning keys of the reference's GPU preconditioners (StandardPreconditioners_gpu_serial.hpp:77-80, 92-96):
+        // accepted and type-checked so that a reference option file loads unchanged; they select between
+        // implementations that do not exist here -- this library always keeps L, D^-1 and U in separate slot rows
+        // ("split_matrix"), has no launch-geometry autotuner ("tune_gpu_kernels": the geometry is fixed by the
+        // layout) and always renumbers by schedule ("reorder")
+        (void)prm.get<bool>("preconditioner.split_matrix", true);
+        (void)prm.get<bool>("preconditioner.tune_gpu_kernels", true);
+        (void)prm.get<bool>("preconditioner.reorder", true);
         s->relaxation = prm.get<double>("preconditioner.relaxation", 1.0);
         s->op_repeats = prm.get<int>("b200.operator_repeats", 1);
         s->throttle = prm.get<int>("b200.throttle_levels", 6);

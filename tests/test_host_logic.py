@@ -189,6 +189,19 @@ def test_unknown_preconditioner_and_solver_are_invalid_argument():
         assert rc == _lib.BAD_OPTIONS and frag in L.opmb200_last_error().decode()
     rc = L.opmb200_create(None, 9, A.n, A.nnzb, A.rowptr, A.col, A.n, None, None, C.byref(h))
     assert rc == _lib.INVALID_ARGUMENT
+    # the tuning keys of the reference's GPU preconditioners (StandardPreconditioners_gpu_serial.hpp:77-80, 92-96) are
+    # accepted and type-checked; mixed precision storage is refused
+    rc = L.opmb200_create(b'{"preconditioner": {"type": "dilu", "split_matrix": "maybe"}}', 3, A.n, A.nnzb, A.rowptr, A.col,
+                          A.n, None, None, C.byref(h))
+    assert rc == _lib.BAD_OPTIONS and "not a bool" in L.opmb200_last_error().decode()
+    rc = L.opmb200_create(b'{"preconditioner": {"type": "dilu", "mixed_precision_scheme": 1}}', 3, A.n, A.nnzb, A.rowptr,
+                          A.col, A.n, None, None, C.byref(h))
+    assert rc == _lib.BAD_OPTIONS and "mixed_precision_scheme" in L.opmb200_last_error().decode()
+    rc = L.opmb200_create(b'{"preconditioner": {"type": "gpudilu", "split_matrix": "true", "tune_gpu_kernels": "false", '
+                          b'"reorder": "true"}}', 3, A.n, A.nnzb, A.rowptr, A.col, A.n, None, None, C.byref(h))
+    assert rc in (_lib.SUCCESS, _lib.CUDA_ERROR), L.opmb200_last_error().decode()  # past the option check (no device here)
+    if rc == _lib.SUCCESS:
+        L.opmb200_destroy(h)
 
 
 def test_add_creator_plugin_hook():
