@@ -441,6 +441,12 @@ struct ReduceCtx {
     double* sums;          // multi-rank over NCCL: the local sums land here, ncclAllReduce and
     int defer;             //   epilogue_kernel follow on the stream (defer != 0)
     const P2PDev* p2p;     // multi-rank over peer memory: the all-reduce happens inside this kernel
+    // a reduction spread over two launches (the SpMV split into interior rows and rows that read ghost values, the
+    // halo copy running beside the first): the first launch only stores its partials (partial_only), the second
+    // stores its own behind them (offset) and its last CTA sums all `total` of them, in index order as ever
+    int offset;
+    int total;
+    int partial_only;
 };
 
 __device__ __forceinline__ void st_sys(double* p, double v)
@@ -617,15 +623,19 @@ __device__ __forceinline__ void grid_reduce(double (&v)[ND], const ReduceCtx& rc
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int d = 0; d < ND; ++d)
-            rc.partials[d * rc.stride + blockIdx.x] = v[d];
-        __threadfence();
-        const unsigned int t = atomicAdd(rc.counter, 1u);
-        is_last = (t == gridDim.x - 1);
+            rc.partials[d * rc.stride + rc.offset + blockIdx.x] = v[d];
+        is_last = false;
+        if (!rc.partial_only) {
+            __threadfence();
+            const unsigned int t = atomicAdd(rc.counter, 1u);
+            is_last = (t == gridDim.x - 1);
+        }
     }
     __syncthreads();
     if (!is_last)
         return;
     __threadfence();
+    const unsigned int nparts = rc.total > 0 ? (unsigned int)rc.total : gridDim.x;
     // the other CTAs' partials must come from the L2 (this SM's L1 may hold the previous reduction's);
     // L1-bypassing loads are slow one by one (~300 cycles each beyond a few in flight), so four
     // partials per strong vector load (rc.stride is a multiple of 4), in a fixed order
@@ -634,7 +644,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[ND], const ReduceCtx& rc
     for (int d = 0; d < ND; ++d) {
         acc[d] = 0.0;
         const double* p = rc.partials + (size_t)d * rc.stride;
-        const unsigned int n4 = gridDim.x >> 2;
+        const unsigned int n4 = nparts >> 2;
         for (unsigned int g = threadIdx.x; g < n4; g += blockDim.x) {
             double w0, w1, w2, w3;
             asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];"
@@ -642,7 +652,7 @@ __device__ __forceinline__ void grid_reduce(double (&v)[ND], const ReduceCtx& rc
                          : "l"(p + 4 * (size_t)g));
             acc[d] += (w0 + w1) + (w2 + w3);
         }
-        for (unsigned int i = (n4 << 2) + threadIdx.x; i < gridDim.x; i += blockDim.x)
+        for (unsigned int i = (n4 << 2) + threadIdx.x; i < nparts; i += blockDim.x)
             acc[d] += __ldcg(p + i);
     }
     __syncthreads();
@@ -728,6 +738,7 @@ __global__ void permute_out_kernel(int64_t n, const int* __restrict__ n2r, const
 // -------------------------------------------------------------------------------------------------
 struct SpmvArgs {
     int nslices;
+    const int* slice_list; // null: all slices in order; else the nslices slices of this launch (interior / boundary pass)
     const SliceMeta* slices;
     const int* slot_col;
     const double* A;
@@ -777,7 +788,7 @@ __global__ void __launch_bounds__(kCtaThreads) spmv_kernel(SpmvArgs a)
     for (int d = 0; d < (NDOT > 0 ? NDOT : 1); ++d)
         dots[d] = 0.0;
     if (S < a.nslices) {
-        const SliceMeta m = a.slices[S];
+        const SliceMeta m = a.slices[a.slice_list ? a.slice_list[S] : S];
         const bool active = lane < m.count;
         const int q = m.q0 + lane;
         const int nsr = m.wl + 1 + m.wu;

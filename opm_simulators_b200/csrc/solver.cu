@@ -184,6 +184,15 @@ struct opmb200_solver {
     bool register_host = true;
     std::vector<std::pair<const void*, size_t>> registered;
 
+    // halo copy overlapped with the interior SpMV (b200.halo_overlap, multi-rank): the copyOwnerToAll that follows a
+    // preconditioner application runs on `stream2` while the SpMV of the slices whose rows read no ghost value runs
+    // on `stream`; the slices that do read ghost values follow once the copy has landed
+    bool halo_overlap = true;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr}; // one pair per half step
+    DevBuf<int> spmv_int_list, spmv_bnd_list;
+    int n_int_slices = 0, n_bnd_slices = 0;
+
     // standard wells kept outside the matrix (opmb200_set_wells): operator = A - C^T D^-1 B
     int n_wells = 0, well_dw = 0;
     std::vector<int32_t> well_ptr_h, well_cells_h; // the structure the device tables were built for
@@ -211,9 +220,11 @@ struct opmb200_solver {
         for (void* pb : peer_base)
             if (pb)
                 cudaIpcCloseMemHandle(pb);
-        for (cudaEvent_t e : {ev0, ev1, ev_iter[0], ev_iter[1], ev_t0, ev_t1})
+        for (cudaEvent_t e : {ev0, ev1, ev_iter[0], ev_iter[1], ev_t0, ev_t1, ev_fork[0], ev_fork[1], ev_join[0], ev_join[1]})
             if (e)
                 cudaEventDestroy(e);
+        if (stream2)
+            cudaStreamDestroy(stream2);
         if (stream)
             cudaStreamDestroy(stream);
     }
@@ -315,11 +326,14 @@ int finish_reduction(opmb200_solver* s, int nd, int epi, int check_done)
 
 // ---- SpMV --------------------------------------------------------------------------------------
 // mode 0: y = A x ; mode 1: y += alpha A x.   ndot/u/epi select the fused dots.
+// phase 0: all slices; 1: the slices that read no ghost value (partials only, no epilogue); 2: the others + the
+// reduction over the partials of both launches
 int launch_spmv(opmb200_solver* s, const double* x, double* y, bool scaleadd, double alpha, int ndot, const double* u,
-                double* copy_out, int epi, int check_done)
+                double* copy_out, int epi, int check_done, int phase = 0)
 {
     SpmvArgs a;
-    a.nslices = s->L.n_slices;
+    a.nslices = phase == 1 ? s->n_int_slices : (phase == 2 ? s->n_bnd_slices : s->L.n_slices);
+    a.slice_list = phase == 1 ? s->spmv_int_list.p : (phase == 2 ? s->spmv_bnd_list.p : nullptr);
     a.slices = s->slices.p;
     a.slot_col = s->slot_col.p;
     a.A = s->A.p;
@@ -332,6 +346,13 @@ int launch_spmv(opmb200_solver* s, const double* x, double* y, bool scaleadd, do
     a.u = u;
     a.copy_out = copy_out;
     a.rc = ndot > 0 ? s->rctx() : ReduceCtx {};
+    const int grid_int = (s->n_int_slices + kWarpsPerCta - 1) / kWarpsPerCta;
+    if (phase == 1) {
+        a.rc.partial_only = 1;
+    } else if (phase == 2) {
+        a.rc.offset = grid_int;
+        a.rc.total = grid_int + (s->n_bnd_slices + kWarpsPerCta - 1) / kWarpsPerCta;
+    }
     a.epi = epi;
     a.sc = s->sc.p;
     a.hist = s->hist.p;
@@ -345,7 +366,7 @@ int launch_spmv(opmb200_solver* s, const double* x, double* y, bool scaleadd, do
     a.well_C = s->w_C.p;
     a.well_z = s->w_z.p;
     a.well_dw = s->well_dw;
-    const int grid = s->slice_grid();
+    const int grid = std::max(1, (a.nslices + kWarpsPerCta - 1) / kWarpsPerCta);
     if (wells) { // z_w = D_w^-1 B_w x first; the perforated rows of the SpMV subtract C^T z_w
         WellZArgs z;
         z.n_wells = s->n_wells;
@@ -380,7 +401,7 @@ int launch_spmv(opmb200_solver* s, const double* x, double* y, bool scaleadd, do
     });
 #undef SPMV_LAUNCH
     TRY(check_launch(s, "spmv"));
-    if (ndot > 0)
+    if (ndot > 0 && phase != 1)
         TRY(finish_reduction(s, ndot, epi, check_done));
     return OPMB200_SUCCESS;
 }
@@ -479,7 +500,9 @@ int launch_sweep(opmb200_solver* s, const SweepArgs& a, bool upper)
 void trace_mark(opmb200_solver* s, const char* name);
 
 // Preconditioner::apply(v, d) on level-ordered device vectors, incl. BlockPreconditioner's halo copy
-int prec_apply(opmb200_solver* s, const double* d, double* v, int ghost_zero, int check_done)
+// defer_halo: the caller runs the halo copy itself (beside the interior SpMV, prec_apply_then_op); the relaxation then
+// comes BEFORE the copy -- every entry is still scaled exactly once, the copies receive the owner's scaled value
+int prec_apply(opmb200_solver* s, const double* d, double* v, int ghost_zero, int check_done, bool defer_halo = false)
 {
     if (s->prec == PREC_NONE) {
         CUDA_TRY(cudaMemcpyAsync(v, d, s->len() * sizeof(double), cudaMemcpyDeviceToDevice, s->stream));
@@ -489,11 +512,44 @@ int prec_apply(opmb200_solver* s, const double* d, double* v, int ghost_zero, in
     TRY(launch_sweep(s, a, false));
     TRY(launch_sweep(s, a, true));
     trace_mark(s, "sweeps");
-    TRY(copy_owner_to_all(s, v));
+    if (!defer_halo)
+        TRY(copy_owner_to_all(s, v));
     if (s->prec == PREC_ILU0 && std::abs(s->relaxation - 1.0) > 1e-15) {
         scale_kernel<<<s->vec_grid, 256, 0, s->stream>>>(s->len(), s->relaxation, v, s->sc.p, check_done);
         TRY(check_launch(s, "relaxation"));
     }
+    return OPMB200_SUCCESS;
+}
+
+// y = W^-1 d (block-Jacobi), out = A y with the fused dots: the two operations every BiCGSTAB half step chains.
+// Multi-rank: the copyOwnerToAll between them runs on a second stream beside the SpMV of the rows that read no ghost
+// value (north_star: "halo rows ... exchanged ... overlapped with interior SpMV"); the reference serialises the two
+// (gpuistl/GpuBlockPreconditioner.hpp:65-81).
+int prec_apply_then_op(opmb200_solver* s, int half, const double* d, double* y, double* out, int ndot, const double* u, int epi)
+{
+    const bool overlap = s->halo_overlap && s->n_ranks > 1 && !s->nb_rank.empty() && s->prec != PREC_NONE
+        && s->op_repeats <= 1 && s->n_wells == 0 && s->n_int_slices > 0 && s->n_bnd_slices > 0 && s->stream2;
+    if (!overlap) {
+        TRY(prec_apply(s, d, y, 1, 1));
+        trace_mark(s, "prec_apply+halo");
+        TRY(op_apply(s, y, out, ndot, u, epi, 1));
+        trace_mark(s, "spmv+allreduce");
+        return OPMB200_SUCCESS;
+    }
+    TRY(prec_apply(s, d, y, 1, 1, true));
+    CUDA_TRY(cudaEventRecord(s->ev_fork[half], s->stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->stream2, s->ev_fork[half], 0));
+    cudaStream_t keep = s->stream;
+    s->stream = s->stream2; // the halo copy is enqueued on the second stream
+    const int rc = copy_owner_to_all(s, y);
+    s->stream = keep;
+    TRY(rc);
+    CUDA_TRY(cudaEventRecord(s->ev_join[half], s->stream2));
+    TRY(launch_spmv(s, y, out, false, 0.0, ndot, u, nullptr, epi, 1, 1)); // rows without ghost neighbours
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->ev_join[half], 0));
+    trace_mark(s, "prec_apply+halo||interior spmv");
+    TRY(launch_spmv(s, y, out, false, 0.0, ndot, u, nullptr, epi, 1, 2)); // rows that read ghost values + the dots
+    trace_mark(s, "boundary spmv+allreduce");
     return OPMB200_SUCCESS;
 }
 
@@ -670,6 +726,7 @@ int parse_options(opmb200_solver* s, const char* json)
         s->register_host = prm.get<int>("b200.register_host_buffers", 1) != 0;
         s->ctas_per_sm = std::max(1, std::min(2, prm.get<int>("b200.ctas_per_sm", 1)));
         s->use_graph = prm.get<int>("b200.cuda_graph", 1) != 0;
+        s->halo_overlap = prm.get<int>("b200.halo_overlap", 1) != 0;
         s->trace = std::getenv("OPMB200_TRACE") != nullptr;
     } catch (const std::exception& e) {
         return fail(OPMB200_BAD_OPTIONS, e.what());
@@ -744,23 +801,17 @@ void trace_report(opmb200_solver* s)
 // one BiCGSTAB iteration (two half steps) enqueued on the stream
 int enqueue_iteration(opmb200_solver* s)
 {
-    const int gz = 1; // Dune: y = 0 before every preconditioner application
+    // (Dune sets y = 0 before every preconditioner application: ghost_zero = 1 in prec_apply_then_op)
     trace_mark(s, "iteration_begin");
     vec_p_update_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, false));
     TRY(check_launch(s, "vec_p_update"));
     trace_mark(s, "vec_p_update");
-    TRY(prec_apply(s, s->vp.p, s->vy.p, gz, 1));                       // y = W^-1 p
-    trace_mark(s, "prec_apply+halo");
-    TRY(op_apply(s, s->vy.p, s->vv.p, 1, s->vrt.p, EPI_H, 1));          // v = A y ; h = (rt, v)
-    trace_mark(s, "spmv+allreduce");
+    TRY(prec_apply_then_op(s, 0, s->vp.p, s->vy.p, s->vv.p, 1, s->vrt.p, EPI_H)); // y = W^-1 p ; v = A y ; h = (rt, v)
     vec_half1_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, true)); // x += alpha y ; r -= alpha v ; |r|
     TRY(check_launch(s, "vec_half1"));
     TRY(finish_reduction(s, 1, EPI_NORM1, 1));
     trace_mark(s, "vec_half+allreduce");
-    TRY(prec_apply(s, s->vr.p, s->vy.p, gz, 1));                       // y = W^-1 r
-    trace_mark(s, "prec_apply+halo");
-    TRY(op_apply(s, s->vy.p, s->vt.p, 2, s->vr.p, EPI_OMEGA, 1));       // t = A y ; (t,r), (t,t)
-    trace_mark(s, "spmv+allreduce");
+    TRY(prec_apply_then_op(s, 1, s->vr.p, s->vy.p, s->vt.p, 2, s->vr.p, EPI_OMEGA)); // y = W^-1 r ; t = A y ; (t,r), (t,t)
     vec_half2_kernel<<<s->vec_grid, 256, 0, s->stream>>>(vec_args(s, true)); // x += omega y ; r -= omega t ; |r| ; (rt,r)
     TRY(check_launch(s, "vec_half2"));
     TRY(finish_reduction(s, 2, EPI_NORM2, 1));
@@ -1170,7 +1221,8 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
         CUDA_TRY(cudaMemsetAsync(v->p, 0, (len + 2) * sizeof(double), st));
     }
     s->vec_grid = (int)std::max<int64_t>(1, std::min<int64_t>((int64_t)s->num_sms * 8, ((int64_t)len + 255) / 256));
-    s->max_grid = (std::max(s->vec_grid, s->slice_grid()) + 3) & ~3; // multiple of 4: grid_reduce reads 4 partials per load
+    // multiple of 4: grid_reduce reads 4 partials per load; + 1: the SpMV split into two launches rounds its CTAs up twice
+    s->max_grid = (std::max(s->vec_grid, s->slice_grid() + 1) + 3) & ~3;
     CUDA_TRY(s->partials.alloc((size_t)2 * s->max_grid));
     CUDA_TRY(s->hist.alloc((size_t)2 * s->maxiter + 4));
     CUDA_TRY(s->sums.alloc(4));
@@ -1189,6 +1241,27 @@ int opmb200_create(const char* json_options, int block_size, int64_t n_rows, int
 
     // ---- halo lists -> positions --------------------------------------------------------------------
     if (s->n_ranks > 1) {
+        { // slices whose rows read no ghost value / the others (interior and boundary pass of the overlapped SpMV)
+            std::vector<int> li, lb;
+            for (int i = 0; i < L.n_slices; ++i) {
+                bool ghost = false;
+                const int64_t g0 = (int64_t)L.slice_base[i] * kSlice;
+                const int64_t g1 = g0 + (int64_t)(L.slice_wl[i] + 1 + L.slice_wu[i]) * kSlice;
+                for (int64_t g = g0; g < g1 && !ghost; ++g)
+                    ghost = L.slot_col[g] >= 0 && L.r2n[L.slot_col[g]] >= n_interior;
+                (ghost ? lb : li).push_back(i);
+            }
+            s->n_int_slices = (int)li.size();
+            s->n_bnd_slices = (int)lb.size();
+            CUDA_TRY(s->spmv_int_list.upload(li, st));
+            CUDA_TRY(s->spmv_bnd_list.upload(lb, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+            for (int h = 0; h < 2; ++h) {
+                CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork[h], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join[h], cudaEventDisableTiming));
+            }
+        }
         const int nn = halo->n_neighbors;
         s->nb_rank.assign(halo->neighbor_rank, halo->neighbor_rank + nn);
         s->send_ptr.assign(halo->send_ptr, halo->send_ptr + nn + 1);

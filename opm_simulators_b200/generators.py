@@ -210,13 +210,15 @@ def laplace_like(n_side: int, b: int, rng, dims: int = 2, asym: float = 0.0) -> 
 
 
 def standard_wells(A: BCSR, n_wells: int = 8, perfs: int = 12, dim_wells: int | None = None, seed: int = 7,
-                   strength: float = 0.02, shared_cells: int = 0):
+                   strength: float = 0.2, shared_cells: int = 0):
     """Synthetic StandardWell equations for the operator A - sum_w C_w^T D_w^-1 B_w
     (wells/StandardWellEquations.hpp: duneB_, duneC_ with one dim_wells x b block per perforation, invDuneD_).
 
     Every well perforates `perfs` cells of a vertical-ish line of rows (stride = a random step), wells may share
     `shared_cells` cells (two wells perforating one cell, which the reference allows).  The blocks are scaled by
-    `strength` relative to the perforated cell's diagonal block so that A - C^T D^-1 B stays well conditioned.
+    `strength` relative to the perforated cell's diagonal block, and C = -(B + 20 % noise) with D close to 2 I, so that
+    -C^T D^-1 B is close to a positive semi-definite addition: A - C^T D^-1 B stays as well conditioned as A (a random
+    sign pattern makes the combined operator indefinite and BiCGSTAB chaotic: 1e-15 on the rhs moved x by 7 %).
     Returns dict(ptr, cells, B, C, Dinv) in the layout of include/opmb200.h (opmb200_set_wells)."""
     rng = np.random.default_rng(seed)
     b = A.b
@@ -243,7 +245,7 @@ def standard_wells(A: BCSR, n_wells: int = 8, perfs: int = 12, dim_wells: int | 
         diag[k] = np.abs(A.val[d]).max()
     scale = np.sqrt(strength * diag)[:, None, None]
     Bm = rng.uniform(-1.0, 1.0, (n_perf, dw, b)) * scale
-    Cm = rng.uniform(-1.0, 1.0, (n_perf, dw, b)) * scale
+    Cm = -(Bm + 0.2 * rng.uniform(-1.0, 1.0, (n_perf, dw, b)) * scale)
     D = rng.uniform(-0.3, 0.3, (n_wells, dw, dw)) + np.eye(dw) * 2.0
     Dinv = np.linalg.inv(D)
     return dict(ptr=np.asarray(ptr, np.int32), cells=cells, B=np.ascontiguousarray(Bm), C=np.ascontiguousarray(Cm),

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--b", type=int, default=3)
     ap.add_argument("--collectives", default="nccl", choices=["nccl", "p2p"])
     ap.add_argument("--schedule", default="auto", choices=["levels", "tiles", "auto"])
+    ap.add_argument("--halo-overlap", type=int, default=1)
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -81,7 +82,7 @@ def main():
         tol = 1e-8
         fs = FlexibleSolver(MatrixAdapter(ls.A, ls.n_interior, comm, ls.halo),
                             {"tol": tol, "maxiter": 200, "preconditioner": {"type": args.prec, "relaxation": 0.9},
-                             "b200": {"schedule": args.schedule}})
+                             "b200": {"schedule": args.schedule, "halo_overlap": args.halo_overlap}})
         if args.collectives == "p2p":  # collectives inside the library's own kernels over peer memory
             def allgather(blob):
                 out = [None] * world

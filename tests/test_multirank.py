@@ -54,3 +54,15 @@ def test_two_rank_block_jacobi_both_schedules(prec, schedule):
     r = launch(2, ["--mode", "gpu", "--prec", prec, "--b", "3", "--collectives", "p2p", "--schedule", schedule],
                29660 + (1 if prec == "ilu0" else 0) + (2 if schedule == "levels" else 0))
     assert r.returncode == 0 and "MGPU_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("collectives", ["nccl", "p2p"])
+def test_two_rank_block_jacobi_serialised_halo(collectives):
+    """b200.halo_overlap = 0: the halo copy and the SpMV on one stream (the default runs the copy beside the SpMV of the
+    rows that read no ghost value; every other two-rank test covers that)"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = launch(2, ["--mode", "gpu", "--prec", "ilu0", "--b", "3", "--collectives", collectives, "--halo-overlap", "0"],
+               29680 + (1 if collectives == "p2p" else 0))
+    assert r.returncode == 0 and "MGPU_WORKER_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
