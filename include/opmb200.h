@@ -252,7 +252,9 @@ int opmb200_get_history(opmb200_solver* s, double* hist, int capacity, int* coun
  * the algorithmic bytes one launch moves (SURVEY.md section 8d formulas).
  * what: 0 SpMV (y = A x), 1 preconditioner apply (lower + upper sweep), 2 preconditioner update
  *       (relayout + factorisation), 3 the fused BiCGSTAB vector kernels of one iteration,
- *       4 lower sweep only, 5 upper sweep only. */
+ *       4 lower sweep only, 5 upper sweep only, 6 (experiment) upper sweep with an SpMV beside it,
+ *       7 CPR quasi-IMPES weights, 8 CPR coarse entries, 9 CPR restriction + prolongation.
+ *       With wells set (opmb200_set_wells), 0 times the well-corrected operator (well kernel + SpMV). */
 int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, double* ms_per_launch,
                         double* algorithmic_bytes);
 

@@ -1654,6 +1654,41 @@ int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, doubl
             TRY(check_launch(s, "vector kernels"));
             bytes = 17 * 8 * b * N;
             break;
+        case 7:   // CPR: quasi-IMPES weights from the diagonal blocks (pressure index 0, rows weighted)
+        case 8:   // CPR: coarse (pressure) matrix entries of every block
+        case 9: { // CPR: restriction of one fine vector + prolongation of one coarse vector
+            const size_t len = (size_t)s->len();
+            if (s->cpr_w.n < len)
+                CUDA_TRY(s->cpr_w.alloc(len));
+            if (s->cpr_coarse.n < (size_t)s->L.nnzb)
+                CUDA_TRY(s->cpr_coarse.alloc((size_t)s->L.nnzb));
+            if (!s->cpr_flag.p)
+                CUDA_TRY(s->cpr_flag.alloc(1));
+            const int grid = s->slice_grid();
+            if (what == 7 || it == 0) { // (the other two need weights: made once)
+                DISPATCH_B(s->b, (cpr_weights_kernel<B, false><<<grid, kCtaThreads, 0, s->stream>>>(
+                                  s->L.n_slices, s->slices.p, s->A.p, s->r2n.p, 0, s->cpr_w.p, s->cpr_flag.p)));
+                TRY(check_launch(s, "cpr_weights"));
+                bytes = 16 * b * b * N / 2 + 8 * b * N + 4 * N; // diagonal blocks read, weights written, r2n
+            }
+            if (what == 8) {
+                DISPATCH_B(s->b, (cpr_coarse_kernel<B, false><<<grid, kCtaThreads, 0, s->stream>>>(
+                                  s->L.n_slices, s->slices.p, s->slot_col.p, s->slot_src.p, s->A.p, s->r2n.p, s->cpr_w.p, 0,
+                                  s->cpr_coarse.p)));
+                TRY(check_launch(s, "cpr_coarse"));
+                bytes = nnzb * (8 * b + 4 + 8) + 8 * b * N + 4 * N; // one column of every block, slot_src, coarse entry out
+            }
+            if (what == 9) {
+                DISPATCH_B(s->b, (cpr_restrict_kernel<B, false><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, s->nat0.p, s->cpr_w.p, 0,
+                                                                                              s->nat1.p)));
+                DISPATCH_B(s->b, (cpr_prolongate_kernel<B, false><<<s->vec_grid, 256, 0, s->stream>>>(s->L.n, s->nat1.p, s->cpr_w.p,
+                                                                                                0, s->nat0.p)));
+                ++s->launches;
+                TRY(check_launch(s, "cpr_restrict+prolongate"));
+                bytes = 2 * 8 * b * N + 8 * N + 8 * N + 8 * N; // fine + weights read, coarse written; coarse read, pressure written
+            }
+            break;
+        }
         default:
             return fail(OPMB200_INVALID_ARGUMENT, "unknown kernel id");
         }

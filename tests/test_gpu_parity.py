@@ -345,6 +345,33 @@ def test_device_pointers_are_accepted():
     assert abs(res.iterations - ro["iterations"]) <= 1 and rel_err(x.cpu().numpy(), xo) < 1e-6
 
 
+def test_device_vectors_through_the_operator_preconditioner_and_dot():
+    """the stand-alone entry points (the preconditioner as a smoother inside a caller's Krylov loop, the operator, the
+    scalar product) on DEVICE vectors: no host copy in either direction (opmb200_precond_apply's 2 H2D +
+    1 D2H per call only apply to host pointers)"""
+    torch = pytest.importorskip("torch")
+    s = generators.config("C3", scale=0.25)
+    A = s["A"]
+    for prec in ("dilu", "ilu0"):
+        fs = FlexibleSolver(MatrixAdapter(A), opts(prec, relaxation=0.9 if prec == "ilu0" else None))
+        d_h = np.random.default_rng(4).standard_normal(A.n * 3)
+        d = torch.from_numpy(d_h).cuda()
+        v = torch.full_like(d, float("nan"))
+        fs.preconditioner().apply(v, d)
+        ps = orc.ParSystem.serial(A.rowptr, A.col, A.val)
+        ps.prec_update(prec, 0.9 if prec == "ilu0" else 1.0)
+        torch.cuda.synchronize()
+        assert rel_err(v.cpu().numpy(), ps.prec_apply([d_h])[0]) < TOL
+        y = torch.full_like(d, float("nan"))
+        fs.op.apply(d, y)
+        assert rel_err(y.cpu().numpy(), orc.spmv(A.rowptr, A.col, A.val, d_h)) < TOL
+        fs.op.applyscaleadd(-2.0, d, y)
+        assert rel_err(y.cpu().numpy(), -orc.spmv(A.rowptr, A.col, A.val, d_h)) < TOL
+        assert abs(fs.dot(d, v) - float(d_h @ v.cpu().numpy())) < 1e-12 * abs(float(d_h @ v.cpu().numpy())) + 1e-12
+        assert torch.equal(d.cpu(), torch.from_numpy(d_h))  # inputs untouched
+        fs.close()
+
+
 def test_wide_rows_beyond_the_register_window():
     """rows with more than 3 lower / upper blocks (NNC- or well-like) take the streaming path"""
     rng = np.random.default_rng(8)
