@@ -49,6 +49,25 @@ def solve(tag):
 
 timed("spmv (no wells)", 0)
 solve("solve_without_wells")
+# marginal cost of one BiCGSTAB iteration: two solves of different length, so that the fixed part of a solve (staging,
+# initial defect, read-back) cancels -- bench.py's iteration_ms divides the whole solve by its iteration count
+marg = []
+for tol in (1e-2, 1e-5):
+    best = None
+    for _ in range(3):
+        x, r = np.zeros(A.n * A.b), s["rhs"].copy()
+        res = fs.apply(x, r, tol)
+        ms = fs.info()["t_solve_ms"]
+        best = ms if best is None else min(best, ms)
+    marg.append((res.iterations, best))
+(i0, t0), (i1, t1) = marg
+b_ = A.b
+b_iter = 2 * (A.nnzb * (8 * b_ * b_ + 4) + 4 * (A.n + 1) + 16 * b_ * A.n) \
+    + 2 * ((A.nnzb - A.n) * (8 * b_ * b_ + 4) + 16 * b_ * b_ * A.n + 40 * b_ * A.n + 16 * (A.n + 1) + 8 * A.n) + 19 * 8 * b_ * A.n
+if i1 > i0:
+    m = (t1 - t0) / (i1 - i0)
+    out["marginal_iteration"] = {"solves": marg, "ms": round(m, 4), "fixed_ms_per_solve": round(t0 - i0 * m, 4),
+                                 "algorithmic_MB": round(b_iter / 1e6, 1), "roofline_frac": round(b_iter / 1e6 / peak / m, 4)}
 # Norne has 36 wells, a full-field model a few hundred: 200 wells x 40 perforations, 4 well equations (black oil)
 wells = generators.standard_wells(A, n_wells=200, perfs=40, seed=5, strength=0.05)
 op.set_wells(wells)
