@@ -520,6 +520,13 @@ __device__ __forceinline__ void tw_rhs(const TwArgs& a, unsigned char* smem, int
         while (ctl[kCtlPublished] < g + 1 - NS) {}
         if (t + 1 < ns) { // the compute warps decode the next step's record while they run this one
             const int g1 = g + 1;
+            // A parity wait is only meaningful against the phase right before: the previous step of THAT stage
+            // (g1 - NS) must be done with, so that its record has landed.  The gate above says so for this step's
+            // stage only -- for the kStages-th step of a chunk the next stage still holds the chunk's FIRST record,
+            // possibly in flight, the wait for the phase after it returned at once and, once in ~1e5 chunks, the
+            // compute warps decoded the stale record (a wrong preconditioner application in ~1 % of the calls on C3,
+            // scripts/determinism_probe2.py).  The loader cannot issue record g1 before this condition either.
+            while (ctl[kCtlPublished] < g1 + 1 - NS) {}
             mbar_wait(data_bar + g1 % NS, (unsigned)(g1 / NS) & 1u);
         }
         TWP_MARK(1);

@@ -70,3 +70,28 @@ def test_c3_full_size_against_the_oracle(c3, prec, schedule):
     res2 = fs.apply(x2_, r2_)
     assert res2.iterations == res.iterations and np.array_equal(x2_, x)
     fs.close()
+
+
+@pytest.mark.parametrize("prec,applies", [("dilu", 400), ("ilu0", 200)])
+def test_tile_walkers_equal_the_level_schedule_on_every_application(c3, prec, applies):
+    """Regression test of a rare hand-over race: the right-hand-side warps' parity wait for the NEXT step's record was
+    not anchored on the phase before it at the kStages-th step of a tile, and once in ~1e5 tiles the compute warps
+    decoded a stale record -- about 1 % of the preconditioner applications on C3 were wrong by 1e-6..3e-3
+    (profiles/r02_determinism.md).  Every application must be bit-identical to the level schedule's."""
+    torch = pytest.importorskip("torch")
+    A = c3["A"]
+    d = torch.from_numpy(np.random.default_rng(3).standard_normal(A.n * 3)).cuda()
+    ref = FlexibleSolver(MatrixAdapter(A), {"preconditioner": {"type": prec}, "b200": {"schedule": "levels"}})
+    v_ref = torch.empty_like(d)
+    ref.preconditioner().apply(v_ref, d)
+    ref.close()
+    fs = FlexibleSolver(MatrixAdapter(A), {"preconditioner": {"type": prec}, "b200": {"schedule": "tiles"}})
+    assert fs.info()["schedule"] == 1
+    v = torch.empty_like(d)
+    wrong = 0
+    for _ in range(applies):
+        v.fill_(float("nan"))
+        fs.preconditioner().apply(v, d)
+        wrong += int(not torch.equal(v, v_ref))
+    fs.close()
+    assert wrong == 0, f"{wrong} of {applies} applications differ from the level schedule"
