@@ -406,6 +406,17 @@ def run_b200(args):
     true = true_residual(fs, w, x_d, rhs_d)
     conv_all = all(D.gather(bool(T["last"].converged)))
     iters_all = D.gather(int(T["last"].iterations))
+    # Dune's iteration count is (int) of a half-step counter: a solve reported as 10 iterations ran 10.5.  The cost of
+    # one iteration is taken (a) from the executed half steps of the timed solves and (b) as the MARGINAL cost between
+    # the timed solve and one long solve (tol 1e-6) of the same system, so that what is fixed per solve (staging, initial
+    # defect, read-back) cancels.
+    half_steps = len(fs.history()) - 1
+    fs.update(vals_d)
+    x_d.zero_()
+    r_d.copy_(rhs_d)
+    torch_.cuda.current_stream().synchronize()
+    fs.apply(x_d, r_d, 1e-6)
+    long_ms, long_half = fs.info()["t_solve_ms"], len(fs.history()) - 1
 
     # ---- end-to-end arms: host buffers through the same calls ----------------------------------------
     nb = args.steps + args.warmup
@@ -508,9 +519,15 @@ def run_b200(args):
             "iterations_per_solve": it_per, "iters_per_s": round(T["iters"] / (T["ms_dev"] * 1e-3), 2),
             "time_to_solve_ms": round(T["ms_dev"] / steps, 4), "wall_ms_per_step": round(T["wall"] * 1e3 / steps, 4),
             "update_ms": round(T["t_upd"], 4), "solve_ms": round(T["t_slv"], 4),
-            "iteration_ms": round(T["t_slv"] / max(it_per, 1), 4),
+            "iteration_ms": round(T["t_slv"] / max(half_steps / 2, 0.5), 4),
+            "iteration_ms_definition": "device time of a solve / executed iterations (half steps / 2), fixed per-solve work included",
+            "iterations_executed_per_solve": half_steps / 2,
             "iteration_algorithmic_MB": round(b_iter / 1e6, 1),
-            "iteration_roofline_frac": round((b_iter / 1e6 / peak) / (T["t_slv"] / max(it_per, 1)), 4),
+            "iteration_roofline_frac": round((b_iter / 1e6 / peak) / (T["t_slv"] / max(half_steps / 2, 0.5)), 4),
+            "iteration_marginal": (None if long_half <= half_steps else {
+                "ms": round((long_ms - T["t_slv"]) / ((long_half - half_steps) / 2), 4),
+                "roofline_frac": round((b_iter / 1e6 / peak) / ((long_ms - T["t_slv"]) / ((long_half - half_steps) / 2)), 4),
+                "from": f"solve to 1e-6: {long_half / 2} iterations in {long_ms:.3f} ms against {half_steps / 2} in {T['t_slv']:.3f} ms"}),
             "e2e": {"value": round(e2e_value, 3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": round(E["wall"] * 1e3 / steps, 4),
                     "device_ms_per_step": round(E["ms_dev"] / steps, 4), "buffers": "pinned host memory",
