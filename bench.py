@@ -482,8 +482,9 @@ def run_b200(args):
                 "traffic": traffic, "traffic_unit": "MB per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "algorithmic_MB_per_launch": round(b_sweep, 1), "peak_source": peak_src, "per_kernel": kern}
     N, nnzb = info0["n_rows"], info0["nnzb"]
-    b_iter = 2 * (nnzb * (8 * b * b + 4) + 4 * (N + 1) + 16 * b * N) \
-        + 2 * ((nnzb - N) * (8 * b * b + 4) + 16 * b * b * N + 40 * b * N + 16 * (N + 1) + 8 * N) + 19 * 8 * b * N
+    b_prec = (nnzb * (8 * b * b + 4) + 32 * b * N + 16 * (N + 1) + 8 * N) if args.prec == "ilu0" \
+        else ((nnzb - N) * (8 * b * b + 4) + 16 * b * b * N + 40 * b * N + 16 * (N + 1) + 8 * N)
+    b_iter = 2 * (nnzb * (8 * b * b + 4) + 4 * (N + 1) + 16 * b * N) + 2 * b_prec + 19 * 8 * b * N
     fs.close()
     del vals_d, rhs_d, x_d, r_d
     torch.cuda.empty_cache()
