@@ -254,7 +254,10 @@ int opmb200_get_history(opmb200_solver* s, double* hist, int capacity, int* coun
  *       (relayout + factorisation), 3 the fused BiCGSTAB vector kernels of one iteration,
  *       4 lower sweep only, 5 upper sweep only, 6 (experiment) upper sweep with an SpMV beside it,
  *       7 CPR quasi-IMPES weights, 8 CPR coarse entries, 9 CPR restriction + prolongation.
- *       With wells set (opmb200_set_wells), 0 times the well-corrected operator (well kernel + SpMV). */
+ *       With wells set (opmb200_set_wells), 0 times the well-corrected operator (well kernel + SpMV).
+ * A measurement aid, not part of the solve path: it overwrites the handle's work vectors and device scalars, and
+ * what = 2 re-runs the last update from its device-resident values (a caller's DEVICE value buffer must still be
+ * alive).  Solves after it are unaffected (every solve re-initialises its state). */
 int opmb200_time_kernel(opmb200_solver* s, int what, int warmup, int reps, double* ms_per_launch,
                         double* algorithmic_bytes);
 
