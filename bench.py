@@ -206,6 +206,12 @@ class Dist:
         return box[0]
 
 
+def workload_string(config, dims, n_cells, prec, tol):
+    """the same text in both arms (the driver compares the two `config.workload` strings)"""
+    return (f"{config} {dims[0]}x{dims[1]}x{dims[2]} ({n_cells} cells, 3x3 BCSR) BiCGSTAB+{prec.upper()} tol={tol}, "
+            f"step = value refresh + refactorisation + solve")
+
+
 def make_solver(D, w, prec, tol, collectives, comm, extra=None):
     from opm_simulators_b200.flexible_solver import FlexibleSolver, MatrixAdapter
 
@@ -509,9 +515,7 @@ def run_b200(args):
             "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": args.warmup, "ms_per_step": round(T["ms_dev"] / steps, 4), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.config} {w['dims'][0]}x{w['dims'][1]}x{w['dims'][2]} "
-                                   f"({n_global} cells, 3x3 BCSR) BiCGSTAB+{args.prec.upper()} tol={args.tol}, "
-                                   f"step = value refresh + refactorisation + solve",
+            "config": {"workload": workload_string(args.config, w["dims"], n_global, args.prec, args.tol),
                        "rhs": "N(0,1)", "cells_per_gpu": int(w["n_interior"]), "levels": info0["n_levels"],
                        "sweep_schedule": "tiles" if tiles else "levels",
                        "l2": "inputs larger than L2 (matrix 560 MB per GPU), no explicit flush",
@@ -609,6 +613,7 @@ def run_reference(args):
 
     s = generators.config(args.config)
     A = s["A"]
+    c_ = generators.CONFIGS[args.config]
     use_ref = orc.ref_available() and A.b == 3
     if use_ref:
         ref = orc.RefMixedSolver(A.rowptr, A.col, A.val, tol=args.tol, maxiter=200, use_dilu=(args.prec == "dilu"))
@@ -635,8 +640,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": args.gpus,
            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": round(dt * 1e3 / steps, 3),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{args.config} {A.n} cells 3x3 BCSR BiCGSTAB+{args.prec.upper()} tol={args.tol}, "
-                                  f"step = factorisation + solve to the reduction"},
+           "config": {"workload": workload_string(args.config, (c_["nx"], c_["ny"], c_["nz"]), A.n, args.prec, args.tol),
+                      "step_detail": "the reference solver takes the values, factorises and solves to the reduction in one call"},
            "iterations_per_solve": iters / steps,
            "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": kind,
                             "sample": f"{what}: each step = factorisation + {iters / steps:g} iterations to tol {args.tol} "
