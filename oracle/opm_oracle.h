@@ -12,7 +12,10 @@
  * dune-istl (>= 2.9, not vendored in /root/reference, see dune.module:12) are restated from
  * the published algorithm and anchored on the reference's call sites -- iteration COUNTS on
  * multi-iteration solves and parallel halo results have no stored numbers in the reference
- * and are therefore "parity unpinned" (DESIGN.md section 3).
+ * and are therefore "parity unpinned" (DESIGN.md section 2).  The same holds for the well operator
+ * (orc_well_apply, orc_par_set_wells) and for the numpy restatements of the CPR transfer pieces in oracle.py: the
+ * reference compares two live implementations (tests/gpuistl/test_GpuPressureTransferPolicy.cpp) and stores no
+ * numbers; they are anchored on dense linear algebra (tests/test_oracle_wells_cpr.py).
  *
  * All matrices are block-CSR exactly as Dune::BCRSMatrix<Opm::MatrixBlock<double,b,b>> lays
  * them out (opm/simulators/linalg/gpuistl/GpuSparseMatrix.cpp:164-167): rowptr[n+1],
